@@ -1,0 +1,322 @@
+// C ABI (include/pypde_b200.h).  Nothing throws across this boundary.
+#include "../../include/pypde_b200.h"
+#include "solver.h"
+#include "tables.h"
+
+#include <cmath>
+#include <stdexcept>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+using namespace pypde;
+
+struct pypde_b200_solver {
+  Solver *impl;
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+void set_error(const std::string &e) {
+  g_last_error = e;
+  fprintf(stderr, "%s\n", e.c_str());
+  fflush(stderr);
+}
+
+KernelConfig make_config(int ndim, int N, int V, int FLUX, int STIFF, int secondOrder,
+                         const void *F, const void *B, const void *S) {
+  KernelConfig c;
+  c.ndim = ndim;
+  c.N = N;
+  c.V = V;
+  c.flux = FLUX;
+  c.stiff = STIFF != 0;
+  c.useF = F != nullptr;
+  c.useB = B != nullptr;
+  c.useS = S != nullptr;
+  c.secondOrder = secondOrder != 0 && c.useF;
+  return c;
+}
+} // namespace
+
+#define API_TRY try {
+#define API_CATCH(ret)                                                                            \
+  }                                                                                               \
+  catch (const std::exception &e) {                                                               \
+    set_error(e.what());                                                                          \
+    return ret;                                                                                   \
+  }                                                                                               \
+  catch (...) {                                                                                   \
+    set_error("pypde_b200: unknown error");                                                       \
+    return ret;                                                                                   \
+  }
+
+extern "C" {
+
+const char *pypde_b200_last_error(void) { return g_last_error.c_str(); }
+
+int pypde_b200_version(int *nvrtc_major, int *nvrtc_minor, int *nvjitlink_major,
+                       int *nvjitlink_minor) {
+  API_TRY
+  int a = 0, b = 0;
+  nvrtc().Version(&a, &b);
+  if (nvrtc_major)
+    *nvrtc_major = a;
+  if (nvrtc_minor)
+    *nvrtc_minor = b;
+  unsigned c = 0, d = 0;
+  jitlink().Version(&c, &d);
+  if (nvjitlink_major)
+    *nvjitlink_major = (int)c;
+  if (nvjitlink_minor)
+    *nvjitlink_minor = (int)d;
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_tables(int N, double *nodes, double *wghts, double *derv, double *endv,
+                      double *dgmat, double *dginv, double *sig, double *wm, double *wminv) {
+  API_TRY
+  BasisTables T = make_tables(N);
+  auto cp = [](double *dst, const std::vector<double> &v) {
+    if (dst)
+      memcpy(dst, v.data(), v.size() * sizeof(double));
+  };
+  cp(nodes, T.nodes);
+  cp(wghts, T.wghts);
+  cp(derv, T.derv);
+  cp(endv, T.endv);
+  cp(dgmat, T.dgmat);
+  cp(dginv, T.dginv);
+  cp(sig, T.sig);
+  for (int k = 0; k < 4; k++) {
+    cp(wm ? wm + (size_t)k * N * N : nullptr, T.wm[k]);
+    cp(wminv ? wminv + (size_t)k * N * N : nullptr, T.wminv[k]);
+  }
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_compile(const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+                       const pypde_b200_devfn *S, int ndim, int N, int V, int FLUX, int STIFF,
+                       int secondOrder, size_t *cubin_bytes, void *cubin_out, size_t cubin_cap) {
+  API_TRY
+  g_last_error.clear();
+  KernelConfig c = make_config(ndim, N, V, FLUX, STIFF, secondOrder, F, B, S);
+  choose_block_shapes(c);
+  std::vector<char> cubin = build_cubin(c, F, B, S);
+  if (cubin_bytes)
+    *cubin_bytes = cubin.size();
+  if (cubin_out && cubin_cap >= cubin.size())
+    memcpy(cubin_out, cubin.data(), cubin.size());
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_create(pypde_b200_solver **out, const pypde_b200_devfn *F,
+                      const pypde_b200_devfn *B, const pypde_b200_devfn *S, const int *nX,
+                      int ndim, const double *dX, double CFL, const int *boundaryTypes, int STIFF,
+                      int FLUX, int N, int V, int secondOrder) {
+  API_TRY
+  g_last_error.clear();
+  if (!out)
+    throw std::runtime_error("pypde_b200_create: null out pointer");
+  *out = nullptr;
+  KernelConfig c = make_config(ndim, N, V, FLUX, STIFF, secondOrder, F, B, S);
+  Solver *s = new Solver(c, F, B, S, nX, dX, CFL, boundaryTypes);
+  *out = new pypde_b200_solver{s};
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_destroy(pypde_b200_solver *s) {
+  API_TRY
+  if (s) {
+    delete s->impl;
+    delete s;
+  }
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_set_stream(pypde_b200_solver *s, void *stream) {
+  API_TRY
+  s->impl->set_stream((CUstream)stream);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_set_state(pypde_b200_solver *s, const double *u_host) {
+  API_TRY
+  s->impl->set_state(u_host);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_get_state(pypde_b200_solver *s, double *u_host) {
+  API_TRY
+  s->impl->get_state(u_host);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_bind_state(pypde_b200_solver *s, void *u_device) {
+  API_TRY
+  s->impl->bind_state((CUdeviceptr)u_device);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_begin(pypde_b200_solver *s, double tf) {
+  API_TRY
+  s->impl->begin(tf);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_step_async(pypde_b200_solver *s) {
+  API_TRY
+  s->impl->step_async();
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_sync(pypde_b200_solver *s, double *t, double *dt, int *nan_found) {
+  API_TRY
+  s->impl->sync(t, dt, nan_found);
+  return 0;
+  API_CATCH(1)
+}
+
+long long pypde_b200_launch_count(const pypde_b200_solver *s) { return s ? s->impl->launches : 0; }
+
+int pypde_b200_read_stage(pypde_b200_solver *s, int which, double *out, size_t cap, size_t *n) {
+  API_TRY
+  size_t m = s->impl->read_stage(which, out, cap);
+  if (n)
+    *n = m;
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_comm_unique_id(void *id128) {
+  API_TRY
+  NcclUniqueId id;
+  int r = nccl().GetUniqueId(&id);
+  if (r != 0)
+    throw std::runtime_error(std::string("ncclGetUniqueId: ") + nccl().GetErrorString(r));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_comm_init(int rank, int nranks, const void *id128) {
+  API_TRY
+  ensure_context();
+  Comm &c = global_comm();
+  if (c.comm)
+    throw std::runtime_error("pypde_b200: communicator already initialised");
+  if (nranks > 1) {
+    NcclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    int r = nccl().CommInitRank(&c.comm, nranks, id, rank);
+    if (r != 0)
+      throw std::runtime_error(std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
+  }
+  c.rank = rank;
+  c.nranks = nranks;
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_comm_finalize(void) {
+  API_TRY
+  Comm &c = global_comm();
+  if (c.comm)
+    nccl().CommDestroy(c.comm);
+  c.comm = nullptr;
+  c.rank = 0;
+  c.nranks = 1;
+  return 0;
+  API_CATCH(1)
+}
+
+// ---------------------------------------------------------------------------
+// The reference's entry points (src/api.h:4-13)
+// ---------------------------------------------------------------------------
+void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *, double *, int),
+                void (*S)(double *, double *), bool useF, bool useB, bool useS, double *_u,
+                double tf, int *_nX, int ndim, double *_dX, double CFL, int *_boundaryTypes,
+                bool STIFF, int FLUX, int N, int V, int ndt, bool secondOrder, double *_ret,
+                int nThreads) {
+  (void)nThreads;
+  try {
+    g_last_error.clear();
+    // api.cpp:21-26: unused callbacks are nulled
+    const pypde_b200_devfn *dF = useF ? (const pypde_b200_devfn *)(void *)F : nullptr;
+    const pypde_b200_devfn *dB = useB ? (const pypde_b200_devfn *)(void *)B : nullptr;
+    const pypde_b200_devfn *dS = useS ? (const pypde_b200_devfn *)(void *)S : nullptr;
+    if ((useF && !dF) || (useB && !dB) || (useS && !dS))
+      throw std::runtime_error("pypde_b200: useF/useB/useS set but the descriptor is NULL");
+    KernelConfig c = make_config(ndim, N, V, FLUX, STIFF, secondOrder, dF, dB, dS);
+    Solver solver(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes);
+
+    const Comm &cm = global_comm();
+    // iterator.cpp:53 prints the thread count; the scheduler here is the GPU grid
+    printf("Using %d B200 GPU%s (nThreads ignored)\n", cm.nranks, cm.nranks > 1 ? "s" : "");
+
+    const size_t n = (size_t)solver.ncell() * V;
+    solver.set_state(_u);
+    solver.begin(tf);
+
+    double t = 0.;
+    int pushCount = 0;
+    // iterator.cpp:99-148
+    while (t < tf) {
+      solver.snapshot_prev();
+      solver.step_async();
+      double dt = 0.;
+      int nan_found = 0;
+      solver.sync(&t, &dt, &nan_found);
+      printf("t = %g\n", t);
+
+      if (t >= double(pushCount + 1) / double(ndt) * tf && pushCount < ndt) {
+        solver.get_state(_ret + (size_t)pushCount * n);
+        pushCount += 1;
+      }
+      if (nan_found || std::isnan(t)) {
+        // iterator.cpp:141-145 (rows clamped to the buffer; the loop stops here
+        // instead of running on with NaNs)
+        printf("NaNs found");
+        if (pushCount < ndt)
+          solver.get_prev(_ret + (size_t)pushCount * n);
+        if (pushCount + 1 < ndt)
+          solver.get_state(_ret + (size_t)(pushCount + 1) * n);
+        break;
+      }
+    }
+    fflush(stdout);
+    // iterator.cpp:150 and the in-place update of _u (api.cpp:18, iterator.cpp:129)
+    solver.get_state(_u);
+    if (ndt >= 1)
+      memcpy(_ret + (size_t)(ndt - 1) * n, _u, n * sizeof(double));
+  } catch (const std::exception &e) {
+    set_error(e.what());
+  } catch (...) {
+    set_error("pypde_b200: unknown error in pde_solver");
+  }
+}
+
+void weno_solver(double *ret, double *_u, int *_nX, int ndim, int N, int V) {
+  try {
+    g_last_error.clear();
+    Solver::weno_only(ret, _u, _nX, ndim, N, V);
+  } catch (const std::exception &e) {
+    set_error(e.what());
+  } catch (...) {
+    set_error("pypde_b200: unknown error in weno_solver");
+  }
+}
+
+} // extern "C"

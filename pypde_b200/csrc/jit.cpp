@@ -1,0 +1,322 @@
+#include "jit.h"
+#include "dyn.h"
+#include "tables.h"
+
+#include <map>
+#include <stdint.h>
+#include <mutex>
+#include <stdexcept>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace pypde {
+
+// kernels.cuh, embedded at build time (see __graft_entry__.build / Makefile)
+static const char *const KERNEL_SOURCE =
+#include "kernels_embed.inc"
+    ;
+
+namespace {
+
+int ipow(int b, int e) {
+  int r = 1;
+  while (e-- > 0)
+    r *= b;
+  return r;
+}
+
+uint64_t fnv1a(const void *data, size_t n, uint64_t h) {
+  const unsigned char *p = (const unsigned char *)data;
+  for (size_t i = 0; i < n; i++) {
+    h ^= p[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+struct Hasher {
+  uint64_t a = 14695981039346656037ull, b = 0x9e3779b97f4a7c15ull;
+  void add(const void *d, size_t n) {
+    a = fnv1a(d, n, a);
+    b = fnv1a(d, n, b ^ (n * 0x100000001b3ull));
+  }
+  void add(const std::string &s) { add(s.data(), s.size()); }
+  std::string hex() const {
+    char buf[40];
+    snprintf(buf, sizeof buf, "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+    return buf;
+  }
+};
+
+std::string cache_dir() {
+  const char *e = getenv("PYPDE_B200_CACHE");
+  std::string d;
+  if (e && *e)
+    d = e;
+  else {
+    char buf[64];
+    snprintf(buf, sizeof buf, "/tmp/pypde_b200_cache-%d", (int)getuid());
+    d = buf;
+  }
+  mkdir(d.c_str(), 0700);
+  return d;
+}
+
+bool read_file(const std::string &path, std::vector<char> &out) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f)
+    return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? n : 0);
+  bool ok = n > 0 && fread(out.data(), 1, n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+
+void write_file_atomic(const std::string &path, const std::vector<char> &data) {
+  char tmp[512];
+  snprintf(tmp, sizeof tmp, "%s.%d.tmp", path.c_str(), (int)getpid());
+  FILE *f = fopen(tmp, "wb");
+  if (!f)
+    return;
+  bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (ok)
+    rename(tmp, path.c_str());
+  else
+    unlink(tmp);
+}
+
+bool fma_enabled() {
+  const char *e = getenv("PYPDE_B200_FMA");
+  return e && *e == '1';
+}
+
+// NVRTC: CUDA source -> LTO-IR
+std::vector<char> nvrtc_to_ltoir(const std::string &src, const char *name,
+                                 const std::vector<std::string> &defines) {
+  const NvrtcApi &rt = nvrtc();
+  nvrtcProgram prog;
+  nvrtcResult r = rt.CreateProgram(&prog, src.c_str(), name, 0, nullptr, nullptr);
+  if (r != NVRTC_SUCCESS)
+    throw std::runtime_error(std::string("nvrtcCreateProgram: ") + rt.GetErrorString(r));
+  std::vector<std::string> opts = {"--gpu-architecture=compute_100a", "-dlto", "-std=c++17",
+                                   "-lineinfo", "--fmad=false"};
+  if (fma_enabled())
+    opts.back() = "--fmad=true";
+  for (const std::string &d : defines)
+    opts.push_back("-D" + d);
+  std::vector<const char *> copts;
+  for (const std::string &o : opts)
+    copts.push_back(o.c_str());
+  r = rt.CompileProgram(prog, (int)copts.size(), copts.data());
+  size_t logn = 0;
+  rt.GetProgramLogSize(prog, &logn);
+  std::string log(logn, '\0');
+  if (logn > 1)
+    rt.GetProgramLog(prog, &log[0]);
+  if (r != NVRTC_SUCCESS) {
+    rt.DestroyProgram(&prog);
+    throw std::runtime_error(std::string("pypde_b200: NVRTC failed on ") + name + ": " +
+                             rt.GetErrorString(r) + "\n" + log);
+  }
+  size_t n = 0;
+  rt.GetLTOIRSize(prog, &n);
+  std::vector<char> out(n);
+  rt.GetLTOIR(prog, out.data());
+  rt.DestroyProgram(&prog);
+  if (n == 0)
+    throw std::runtime_error(std::string("pypde_b200: NVRTC produced no LTO-IR for ") + name);
+  return out;
+}
+
+std::string jl_log(JitLinkHandle h) {
+  const JitLinkApi &jl = jitlink();
+  std::string s;
+  size_t n = 0;
+  if (jl.GetErrorLogSize(h, &n) == 0 && n > 1) {
+    std::string e(n, '\0');
+    jl.GetErrorLog(h, &e[0]);
+    s += e.c_str();
+  }
+  n = 0;
+  if (jl.GetInfoLogSize(h, &n) == 0 && n > 1) {
+    std::string e(n, '\0');
+    jl.GetInfoLog(h, &e[0]);
+    s += e.c_str();
+  }
+  return s;
+}
+
+std::mutex g_cache_mutex;
+std::map<std::string, std::vector<char>> g_cache;
+
+} // namespace
+
+void choose_block_shapes(KernelConfig &c) {
+  const int Nd = ipow(c.N, c.ndim);
+  const int NT = c.N * Nd;
+  const int NP = c.N * ipow(c.N, c.ndim - 1);
+  if (NT > 1024)
+    throw std::runtime_error("pypde_b200: order too high for this ndim (N^(ndim+1) > 1024)");
+  // k_dg: NT threads per cell; (2+ndim)*NT*V doubles of shared memory per cell
+  const size_t sm_cell = (size_t)(2 + c.ndim) * NT * c.V * 8;
+  int cpb = 256 / NT;
+  if (cpb < 1)
+    cpb = 1;
+  while (cpb > 1 && cpb * sm_cell > 64 * 1024)
+    cpb--;
+  if (cpb * sm_cell > 220 * 1024)
+    throw std::runtime_error("pypde_b200: predictor working set exceeds shared memory "
+                             "(N^(ndim+1) * V too large)");
+  c.dg_cpb = cpb;
+  // k_faces: NP threads per face; FLX_W*V doubles per thread
+  const size_t sm_pt = (size_t)(c.useB ? 2 : 1) * c.V * 8;
+  int fpb = 128 / NP;
+  if (fpb < 1)
+    fpb = 1;
+  while (fpb > 1 && (size_t)fpb * NP * sm_pt > 48 * 1024)
+    fpb--;
+  c.faces_fpb = fpb;
+}
+
+std::vector<std::string> specialisation_defines(const KernelConfig &c) {
+  auto kv = [](const char *k, int v) {
+    char b[64];
+    snprintf(b, sizeof b, "%s=%d", k, v);
+    return std::string(b);
+  };
+  return {kv("PDE_NDIM", c.ndim),
+          kv("PDE_N", c.N),
+          kv("PDE_V", c.V),
+          kv("PDE_FLUX", c.flux),
+          kv("PDE_STIFF", c.stiff ? 1 : 0),
+          kv("PDE_USE_F", c.useF ? 1 : 0),
+          kv("PDE_USE_B", c.useB ? 1 : 0),
+          kv("PDE_USE_S", c.useS ? 1 : 0),
+          kv("PDE_SECOND_ORDER", c.secondOrder ? 1 : 0),
+          kv("PDE_DG_CPB", c.dg_cpb),
+          kv("PDE_FACES_FPB", c.faces_fpb)};
+}
+
+std::string specialised_source(const KernelConfig &c) {
+  std::string s = tables_cuda_source(make_tables(c.N));
+  s += KERNEL_SOURCE;
+  return s;
+}
+
+std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F,
+                              const pypde_b200_devfn *B, const pypde_b200_devfn *S) {
+  const std::string src = specialised_source(cfg);
+  const std::vector<std::string> defs = specialisation_defines(cfg);
+  const pypde_b200_devfn *fn[3] = {cfg.useF ? F : nullptr, cfg.useB ? B : nullptr,
+                                   cfg.useS ? S : nullptr};
+  const char *fn_names[3] = {"user_F", "user_B", "user_S"};
+
+  Hasher h;
+  h.add(src);
+  for (const std::string &d : defs)
+    h.add(d);
+  h.add(fma_enabled() ? "fma1" : "fma0");
+  for (int i = 0; i < 3; i++) {
+    if (!fn[i]) {
+      h.add("-");
+      continue;
+    }
+    if (!fn[i]->image || fn[i]->bytes == 0)
+      throw std::runtime_error(std::string("pypde_b200: empty device-function image for ") +
+                               fn_names[i]);
+    h.add(&fn[i]->kind, sizeof(int));
+    h.add(fn[i]->image, fn[i]->bytes);
+  }
+  const std::string key = h.hex();
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    auto it = g_cache.find(key);
+    if (it != g_cache.end())
+      return it->second;
+  }
+  const bool use_disk = !(getenv("PYPDE_B200_NO_DISK_CACHE"));
+  const std::string path = cache_dir() + "/" + key + ".cubin";
+  std::vector<char> cubin;
+  if (use_disk && read_file(path, cubin)) {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    g_cache[key] = cubin;
+    return cubin;
+  }
+
+  // 1. our kernels -> LTO-IR
+  std::vector<char> kernels_ir = nvrtc_to_ltoir(src, "pypde_b200_kernels.cu", defs);
+
+  // 2. link with the user functions
+  const JitLinkApi &jl = jitlink();
+  std::vector<const char *> lopts = {"-arch=sm_100a", "-lto", "-O3", "-lineinfo"};
+  lopts.push_back(fma_enabled() ? "-fma=1" : "-fma=0");
+  JitLinkHandle lh = nullptr;
+  int rc = jl.Create(&lh, (unsigned)lopts.size(), lopts.data());
+  if (rc != 0)
+    throw std::runtime_error("pypde_b200: nvJitLinkCreate failed (code " + std::to_string(rc) +
+                             ")" + (lh ? "\n" + jl_log(lh) : ""));
+  auto fail = [&](const std::string &what, int code) {
+    std::string log = jl_log(lh);
+    jl.Destroy(&lh);
+    throw std::runtime_error("pypde_b200: " + what + " failed (code " + std::to_string(code) +
+                             ")\n" + log);
+  };
+  rc = jl.AddData(lh, JITLINK_INPUT_LTOIR, kernels_ir.data(), kernels_ir.size(),
+                  "pypde_b200_kernels");
+  if (rc != 0)
+    fail("nvJitLinkAddData(kernels)", rc);
+  for (int i = 0; i < 3; i++) {
+    if (!fn[i])
+      continue;
+    const char *label = fn[i]->name ? fn[i]->name : fn_names[i];
+    if (fn[i]->kind == PYPDE_B200_LTOIR) {
+      rc = jl.AddData(lh, JITLINK_INPUT_LTOIR, fn[i]->image, fn[i]->bytes, label);
+    } else if (fn[i]->kind == PYPDE_B200_PTX) {
+      rc = jl.AddData(lh, JITLINK_INPUT_PTX, fn[i]->image, fn[i]->bytes, label);
+    } else if (fn[i]->kind == PYPDE_B200_CUDA_SOURCE) {
+      std::string usrc((const char *)fn[i]->image,
+                       strnlen((const char *)fn[i]->image, fn[i]->bytes));
+      std::vector<char> ir;
+      try {
+        ir = nvrtc_to_ltoir(usrc, label, defs);
+      } catch (...) {
+        jl.Destroy(&lh);
+        throw;
+      }
+      rc = jl.AddData(lh, JITLINK_INPUT_LTOIR, ir.data(), ir.size(), label);
+    } else {
+      jl.Destroy(&lh);
+      throw std::runtime_error(std::string("pypde_b200: unknown device-function kind for ") +
+                               fn_names[i]);
+    }
+    if (rc != 0)
+      fail(std::string("nvJitLinkAddData(") + fn_names[i] + ")", rc);
+  }
+  rc = jl.Complete(lh);
+  if (rc != 0)
+    fail("nvJitLinkComplete (is a user_F/user_B/user_S symbol missing or mis-typed?)", rc);
+  size_t n = 0;
+  rc = jl.GetLinkedCubinSize(lh, &n);
+  if (rc != 0 || n == 0)
+    fail("nvJitLinkGetLinkedCubinSize", rc);
+  cubin.resize(n);
+  rc = jl.GetLinkedCubin(lh, cubin.data());
+  if (rc != 0)
+    fail("nvJitLinkGetLinkedCubin", rc);
+  jl.Destroy(&lh);
+
+  if (use_disk)
+    write_file_atomic(path, cubin);
+  std::lock_guard<std::mutex> lk(g_cache_mutex);
+  g_cache[key] = cubin;
+  return cubin;
+}
+
+} // namespace pypde

@@ -1,0 +1,36 @@
+// Run-time specialisation of the kernels and LTO link with the user functions.
+//
+// Reference counterpart: pypde/cfuncs.py:30-75 compiles the user's F/B/S to CPU
+// callbacks with numba; here they arrive as device code (LTO-IR from numba's
+// CUDA target or nvcc -dlto, PTX, or CUDA source) and are linked *into* the
+// hand-written kernels for sm_100a, so every call is inlined.
+#pragma once
+#include "../../include/pypde_b200.h"
+#include <string>
+#include <vector>
+
+namespace pypde {
+
+struct KernelConfig {
+  int ndim = 1, N = 2, V = 1, flux = 0;
+  bool stiff = false, useF = false, useB = false, useS = false, secondOrder = false;
+  int dg_cpb = 1;    // cells per block in k_dg
+  int faces_fpb = 1; // faces per block in k_faces
+};
+
+// Chooses the block shapes for a configuration (threads <= 256 where possible,
+// shared memory within the 227 KB of an sm_100 CTA).
+void choose_block_shapes(KernelConfig &c);
+
+// Returns the linked sm_100a cubin.  Throws std::runtime_error carrying the
+// NVRTC / nvJitLink log on failure.  Results are cached in memory and on disk
+// ($PYPDE_B200_CACHE, default /tmp/pypde_b200_cache-<uid>).
+std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F,
+                              const pypde_b200_devfn *B, const pypde_b200_devfn *S);
+
+// The specialised CUDA source (tables + macros + kernels), for diagnostics and
+// for the offline nvcc build check.
+std::string specialised_source(const KernelConfig &cfg);
+std::vector<std::string> specialisation_defines(const KernelConfig &cfg);
+
+} // namespace pypde

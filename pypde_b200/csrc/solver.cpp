@@ -1,0 +1,543 @@
+#include "solver.h"
+
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace pypde {
+
+namespace {
+int ipow(int b, int e) {
+  int r = 1;
+  while (e-- > 0)
+    r *= b;
+  return r;
+}
+} // namespace
+
+void check(CUresult r, const char *what) {
+  if (r == CUDA_SUCCESS)
+    return;
+  const char *s = nullptr;
+  driver().GetErrorString(r, &s);
+  throw std::runtime_error(std::string("pypde_b200: ") + what + ": " + (s ? s : "unknown CUDA error"));
+}
+
+void ensure_context() {
+  const DriverApi &d = driver();
+  CUcontext ctx = nullptr;
+  check(d.CtxGetCurrent(&ctx), "cuCtxGetCurrent");
+  if (ctx)
+    return;
+  int dev = 0;
+  const char *e = getenv("PYPDE_B200_DEVICE");
+  if (!e || !*e)
+    e = getenv("LOCAL_RANK");
+  if (e && *e)
+    dev = atoi(e);
+  int n = 0;
+  check(d.DeviceGetCount(&n), "cuDeviceGetCount");
+  if (n == 0)
+    throw std::runtime_error("pypde_b200: no CUDA device visible (this library has no CPU path)");
+  if (dev >= n)
+    dev = dev % n;
+  CUdevice cd;
+  check(d.DeviceGet(&cd, dev), "cuDeviceGet");
+  check(d.DevicePrimaryCtxRetain(&ctx, cd), "cuDevicePrimaryCtxRetain");
+  check(d.CtxSetCurrent(ctx), "cuCtxSetCurrent");
+}
+
+Comm &global_comm() {
+  static Comm c;
+  return c;
+}
+
+void DeviceBuffer::alloc(size_t n) {
+  release();
+  if (n == 0)
+    n = 8;
+  check(driver().MemAlloc(&p, n), "cuMemAlloc");
+  bytes = n;
+}
+void DeviceBuffer::release() {
+  if (p) {
+    driver().MemFree(p);
+    p = 0;
+    bytes = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+               const pypde_b200_devfn *S) {
+  std::vector<char> cubin = build_cubin(cfg, F, B, S);
+  ensure_context();
+  const DriverApi &d = driver();
+  check(d.ModuleLoadData(&mod, cubin.data()), "cuModuleLoadData (is this GPU sm_100?)");
+  auto get = [&](CUfunction &f, const char *name) {
+    check(d.ModuleGetFunction(&f, mod, name), name);
+  };
+  get(k_boundaries, "k_boundaries");
+  get(k_weno_sweep, "k_weno_sweep");
+  get(k_cfl, "k_cfl");
+  get(k_dt, "k_dt");
+  get(k_advance, "k_advance");
+  get(k_dg, "k_dg");
+  get(k_faces, "k_faces");
+  get(k_update, "k_update");
+}
+
+Module::~Module() {
+  if (mod)
+    driver().ModuleUnload(mod);
+}
+
+// ---------------------------------------------------------------------------
+Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+               const pypde_b200_devfn *S, const int *nX, const double *dX, double cfl,
+               const int *bt)
+    : cfg_(cfg), cfl_(cfl) {
+  if (cfg_.ndim < 1 || cfg_.ndim > 3)
+    throw std::runtime_error("pypde_b200: ndim must be 1, 2 or 3");
+  if (cfg_.V < 1)
+    throw std::runtime_error("pypde_b200: V must be >= 1");
+  if (cfg_.N < 1)
+    throw std::runtime_error("pypde_b200: order N must be >= 1");
+  if (cfg_.stiff)
+    throw std::runtime_error("pypde_b200: the stiff (Newton-Krylov) predictor is not built yet; "
+                             "pass stiff=False");
+  if (cfg_.flux != 0 && cfg_.useF)
+    throw std::runtime_error("pypde_b200: only flux='rusanov' is built yet");
+  choose_block_shapes(cfg_);
+  ensure_context();
+  const DriverApi &d = driver();
+  CUdevice dev;
+  check(d.CtxGetDevice(&dev), "cuCtxGetDevice");
+  d.DeviceGetAttribute(&sms_, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+  if (sms_ <= 0)
+    sms_ = 148;
+
+  mod_ = std::make_shared<Module>(cfg_, F, B, S);
+
+  const int nd = cfg_.ndim, N = cfg_.N, V = cfg_.V;
+  memset(&g_, 0, sizeof g_);
+  for (int i = 0; i < 3; i++) {
+    g_.nX[i] = 1;
+    g_.dX[i] = 1.;
+  }
+  ncell_ = 1;
+  ncellw_ = 1;
+  long ncellb = 1;
+  for (int i = 0; i < nd; i++) {
+    if (nX[i] < 1)
+      throw std::runtime_error("pypde_b200: empty grid axis");
+    g_.nX[i] = nX[i];
+    g_.dX[i] = dX[i];
+    g_.bt[i] = bt[i];
+    ncell_ *= nX[i];
+    ncellw_ *= nX[i] + 2;
+    ncellb *= nX[i] + 2 * N;
+  }
+  rowlen_ = ncell_ / nX[0];
+
+  const Comm &cm = global_comm();
+  if (cm.nranks > 1) {
+    if (nX[0] < N)
+      throw std::runtime_error("pypde_b200: a slab needs at least N rows along axis 0");
+    const bool periodic = bt[0] == 1;
+    g_.halo_lo = (cm.rank > 0 || periodic) ? 2 : 0;
+    g_.halo_hi = (cm.rank < cm.nranks - 1 || periodic) ? 2 : 0;
+  } else {
+    g_.halo_lo = g_.halo_hi = bt[0] == 1 ? 1 : 0;
+  }
+
+  const int Nd = ipow(N, nd);
+  const int NP = N * ipow(N, nd - 1);
+  const int TRW = 1 + (cfg_.secondOrder ? nd : 0);
+  const size_t D = sizeof(double);
+  halo_lo_.alloc((size_t)N * rowlen_ * V * D);
+  halo_hi_.alloc((size_t)N * rowlen_ * V * D);
+  ub_.alloc((size_t)ncellb * V * D);
+  // WENO intermediates
+  {
+    long shape[3];
+    for (int i = 0; i < nd; i++)
+      shape[i] = nX[i] + 2 * N;
+    size_t sizes[3] = {0, 0, 0};
+    for (int dd = 0; dd < nd; dd++) {
+      shape[dd] -= 2 * (N - 1);
+      size_t n = (size_t)ipow(N, dd + 1) * V;
+      for (int i = 0; i < nd; i++)
+        n *= shape[i];
+      sizes[dd] = n;
+    }
+    if (nd >= 2)
+      tmpA_.alloc(sizes[0] * D);
+    if (nd >= 3)
+      tmpB_.alloc(sizes[1] * D);
+    w_.alloc((size_t)ncellw_ * Nd * V * D);
+  }
+  traces_.alloc((size_t)ncellw_ * 2 * nd * NP * TRW * V * D);
+  centers_.alloc((size_t)ncellw_ * V * D);
+  const int FLXW = cfg_.useB ? 2 : 1;
+  for (int dd = 0; dd < nd; dd++) {
+    long nf = 1;
+    for (int i = 0; i < nd; i++)
+      nf *= nX[i] + (i == dd ? 1 : 0);
+    nfaces_[dd] = nf;
+    flx_[dd].alloc((size_t)nf * FLXW * V * D);
+  }
+  state_.alloc(sizeof(StepState));
+  check(d.MemAllocHost((void **)&h_state_, sizeof(StepState)), "cuMemAllocHost");
+  memset(h_state_, 0, sizeof(StepState));
+
+  check(d.StreamCreate(&stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+  own_stream_ = true;
+
+  // dynamic shared memory opt-in
+  const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;
+  if (dg_smem > 48 * 1024)
+    check(d.FuncSetAttribute(mod_->k_dg, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                             (int)dg_smem),
+          "cuFuncSetAttribute(k_dg smem)");
+}
+
+Solver::~Solver() {
+  const DriverApi &d = driver();
+  if (stream_)
+    d.StreamSynchronize(stream_);
+  if (own_stream_ && stream_)
+    d.StreamDestroy(stream_);
+  if (h_state_)
+    d.MemFreeHost(h_state_);
+}
+
+void Solver::set_stream(CUstream s) {
+  const DriverApi &d = driver();
+  if (stream_)
+    check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+  if (own_stream_ && stream_)
+    d.StreamDestroy(stream_);
+  stream_ = s;
+  own_stream_ = false;
+}
+
+void Solver::set_state(const double *u_host) {
+  ensure_context();
+  if (!u_) {
+    u_own_.alloc((size_t)ncell_ * cfg_.V * sizeof(double));
+    u_ = u_own_.p;
+  }
+  const DriverApi &d = driver();
+  check(d.MemcpyHtoDAsync(u_, u_host, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
+        "cuMemcpyHtoDAsync(u)");
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+}
+
+void Solver::get_state(double *u_host) {
+  ensure_context();
+  if (!u_)
+    throw std::runtime_error("pypde_b200: no state set");
+  const DriverApi &d = driver();
+  check(d.MemcpyDtoHAsync(u_host, u_, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
+        "cuMemcpyDtoHAsync(u)");
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+}
+
+void Solver::bind_state(CUdeviceptr u) {
+  u_own_.release();
+  u_ = u;
+}
+
+void Solver::snapshot_prev() {
+  if (!uprev_.p)
+    uprev_.alloc((size_t)ncell_ * cfg_.V * sizeof(double));
+  check(driver().MemcpyDtoDAsync(uprev_.p, u_, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
+        "cuMemcpyDtoDAsync(uprev)");
+}
+
+void Solver::get_prev(double *u_host) {
+  if (!uprev_.p)
+    throw std::runtime_error("pypde_b200: no previous state kept");
+  const DriverApi &d = driver();
+  check(d.MemcpyDtoHAsync(u_host, uprev_.p, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
+        "cuMemcpyDtoHAsync(uprev)");
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+}
+
+void Solver::begin(double tf) {
+  ensure_context();
+  if (!u_)
+    throw std::runtime_error("pypde_b200: set or bind a state before begin()");
+  StepState s;
+  memset(&s, 0, sizeof s);
+  s.t = 0.;
+  s.dt = 0.;
+  s.tf = tf;
+  s.cfl = cfl_;
+  *h_state_ = s;
+  const DriverApi &d = driver();
+  check(d.MemcpyHtoDAsync(state_.p, h_state_, sizeof(StepState), stream_), "cuMemcpyHtoDAsync(state)");
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+}
+
+unsigned Solver::grid_for(long total, unsigned block) const {
+  long blocks = (total + block - 1) / block;
+  long cap = (long)sms_ * 16;
+  if (blocks > cap)
+    blocks = cap;
+  if (blocks < 1)
+    blocks = 1;
+  return (unsigned)blocks;
+}
+
+void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args) {
+  check(driver().LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr),
+        "cuLaunchKernel");
+  launches++;
+}
+
+void Solver::exchange_halos() {
+  const Comm &cm = global_comm();
+  if (cm.nranks <= 1)
+    return;
+  const NcclApi &nc = nccl();
+  const int N = cfg_.N, V = cfg_.V;
+  const size_t cnt = (size_t)N * rowlen_ * V;
+  const bool periodic = g_.bt[0] == 1;
+  const int lo = cm.rank > 0 ? cm.rank - 1 : (periodic ? cm.nranks - 1 : -1);
+  const int hi = cm.rank < cm.nranks - 1 ? cm.rank + 1 : (periodic ? 0 : -1);
+  const CUdeviceptr first_rows = u_;
+  const CUdeviceptr last_rows = u_ + ((size_t)(g_.nX[0] - N) * rowlen_ * V) * sizeof(double);
+  auto ok = [&](int r, const char *what) {
+    if (r != 0)
+      throw std::runtime_error(std::string("pypde_b200: NCCL ") + what + ": " + nc.GetErrorString(r));
+  };
+  ok(nc.GroupStart(), "ncclGroupStart");
+  if (lo >= 0) {
+    ok(nc.Send((const void *)first_rows, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclSend");
+    ok(nc.Recv((void *)halo_lo_.p, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclRecv");
+  }
+  if (hi >= 0) {
+    ok(nc.Send((const void *)last_rows, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclSend");
+    ok(nc.Recv((void *)halo_hi_.p, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclRecv");
+  }
+  ok(nc.GroupEnd(), "ncclGroupEnd");
+}
+
+// runs the ndim sweeps; shape_in = padded shape of `in`; bufs[d] = output of sweep d
+void Solver::run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs) {
+  const int nd = cfg_.ndim, N = cfg_.N, V = cfg_.V;
+  long shape[3];
+  for (int i = 0; i < nd; i++)
+    shape[i] = shape_in[i];
+  CUdeviceptr cur = in;
+  for (int dd = 0; dd < nd; dd++) {
+    long n1 = 1, n3 = 1;
+    for (int i = 0; i < dd; i++)
+      n1 *= shape[i];
+    for (int i = dd + 1; i < nd; i++)
+      n3 *= shape[i];
+    int md = (int)shape[dd];
+    long n34 = n3 * ipow(N, dd);
+    int n1i = (int)n1;
+    long total = n1 * (md - 2 * (N - 1)) * n34 * V;
+    CUdeviceptr out = bufs[dd];
+    void *args[] = {&cur, &out, &n1i, &md, &n34};
+    launch(mod_->k_weno_sweep, grid_for(total, 256), 256, 0, args);
+    cur = out;
+    shape[dd] -= 2 * (N - 1);
+  }
+}
+
+void Solver::step_async() {
+  ensure_context();
+  const int nd = cfg_.ndim, N = cfg_.N, V = cfg_.V;
+  const int Nd = ipow(N, nd);
+  const Comm &cm = global_comm();
+
+  exchange_halos();
+  {
+    long total = 1;
+    for (int i = 0; i < nd; i++)
+      total *= g_.nX[i] + 2 * N;
+    total *= V;
+    void *args[] = {&u_, &halo_lo_.p, &halo_hi_.p, &ub_.p, &g_};
+    launch(mod_->k_boundaries, grid_for(total, 256), 256, 0, args);
+  }
+  {
+    long shape[3];
+    for (int i = 0; i < nd; i++)
+      shape[i] = g_.nX[i] + 2 * N;
+    CUdeviceptr bufs[3];
+    if (nd == 1)
+      bufs[0] = w_.p;
+    else if (nd == 2) {
+      bufs[0] = tmpA_.p;
+      bufs[1] = w_.p;
+    } else {
+      bufs[0] = tmpA_.p;
+      bufs[1] = tmpB_.p;
+      bufs[2] = w_.p;
+    }
+    run_sweeps(ub_.p, shape, bufs);
+  }
+  {
+    void *args[] = {&w_.p, &ncellw_, &g_, &state_.p};
+    launch(mod_->k_cfl, grid_for(ncellw_, 128), 128, 0, args);
+  }
+  if (cm.nranks > 1) {
+    const NcclApi &nc = nccl();
+    CUdeviceptr mb = state_.p + offsetof(StepState, maxbits);
+    int r = nc.AllReduce((const void *)mb, (void *)mb, 1, NCCL_UINT64, NCCL_MAX, cm.comm, stream_);
+    if (r != 0)
+      throw std::runtime_error(std::string("pypde_b200: ncclAllReduce: ") + nc.GetErrorString(r));
+  }
+  {
+    void *args[] = {&state_.p};
+    launch(mod_->k_dt, 1, 1, 0, args);
+  }
+  {
+    const unsigned block = cfg_.dg_cpb * N * Nd;
+    const size_t smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * sizeof(double);
+    long nblocks = (ncellw_ + cfg_.dg_cpb - 1) / cfg_.dg_cpb;
+    long cap = (long)sms_ * 32;
+    if (nblocks > cap)
+      nblocks = cap;
+    void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
+    launch(mod_->k_dg, (unsigned)nblocks, block, smem, args);
+  }
+  if (cfg_.useF || cfg_.useB) {
+    const int NP = N * ipow(N, nd - 1);
+    const int FLXW = cfg_.useB ? 2 : 1;
+    for (int dd = 0; dd < nd; dd++) {
+      const unsigned block = cfg_.faces_fpb * NP;
+      const size_t smem = (size_t)cfg_.faces_fpb * NP * FLXW * V * sizeof(double);
+      long nblocks = (nfaces_[dd] + cfg_.faces_fpb - 1) / cfg_.faces_fpb;
+      long cap = (long)sms_ * 32;
+      if (nblocks > cap)
+        nblocks = cap;
+      void *args[] = {&traces_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
+      launch(mod_->k_faces, (unsigned)nblocks, block, smem, args);
+    }
+  }
+  {
+    FluxPtrs fp;
+    for (int i = 0; i < 3; i++)
+      fp.f[i] = flx_[i < nd ? i : 0].p;
+    void *args[] = {&u_, &centers_.p, &fp, &g_, &state_.p};
+    launch(mod_->k_update, grid_for(ncell_ * V, 256), 256, 0, args);
+  }
+  {
+    void *args[] = {&state_.p};
+    launch(mod_->k_advance, 1, 1, 0, args);
+  }
+}
+
+void Solver::sync(double *t, double *dt, int *nan_found) {
+  ensure_context();
+  const DriverApi &d = driver();
+  check(d.MemcpyDtoHAsync(h_state_, state_.p, sizeof(StepState), stream_), "cuMemcpyDtoHAsync(state)");
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize (a kernel failed?)");
+  if (t)
+    *t = h_state_->t;
+  if (dt)
+    *dt = h_state_->dt;
+  if (nan_found)
+    *nan_found = h_state_->nan_flag;
+}
+
+size_t Solver::read_stage(int which, double *out, size_t cap) {
+  ensure_context();
+  const DeviceBuffer *b = nullptr;
+  switch (which) {
+  case 0:
+    b = &ub_;
+    break;
+  case 1:
+    b = &w_;
+    break;
+  case 2:
+    b = &traces_;
+    break;
+  case 3:
+    b = &centers_;
+    break;
+  default:
+    if (which >= 4 && which < 4 + cfg_.ndim)
+      b = &flx_[which - 4];
+  }
+  if (!b || !b->p)
+    throw std::runtime_error("pypde_b200: unknown stage");
+  size_t n = b->bytes / sizeof(double);
+  size_t m = n < cap ? n : cap;
+  const DriverApi &d = driver();
+  if (m && out) {
+    check(d.MemcpyDtoHAsync(out, b->p, m * sizeof(double), stream_), "cuMemcpyDtoHAsync(stage)");
+    check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V) {
+  if (ndim < 1 || ndim > 3)
+    throw std::runtime_error("pypde_b200: weno_solver supports ndim 1..3");
+  KernelConfig cfg;
+  cfg.ndim = ndim;
+  cfg.N = N;
+  cfg.V = V;
+  choose_block_shapes(cfg);
+  ensure_context();
+  const DriverApi &d = driver();
+  Module mod(cfg, nullptr, nullptr, nullptr);
+  int sms = 148;
+  long shape[3] = {1, 1, 1};
+  size_t nin = V;
+  for (int i = 0; i < ndim; i++) {
+    shape[i] = nX[i];
+    nin *= nX[i];
+    if (nX[i] < 2 * N - 1)
+      throw std::runtime_error("pypde_b200: weno_solver needs at least 2N-1 cells per axis");
+  }
+  CUstream st;
+  check(d.StreamCreate(&st, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+  DeviceBuffer in, buf[2];
+  in.alloc(nin * sizeof(double));
+  check(d.MemcpyHtoDAsync(in.p, u, nin * sizeof(double), st), "cuMemcpyHtoDAsync");
+  CUdeviceptr cur = in.p;
+  size_t nout = nin;
+  for (int dd = 0; dd < ndim; dd++) {
+    long n1 = 1, n3 = 1;
+    for (int i = 0; i < dd; i++)
+      n1 *= shape[i];
+    for (int i = dd + 1; i < ndim; i++)
+      n3 *= shape[i];
+    int md = (int)shape[dd];
+    long n34 = n3 * ipow(N, dd);
+    int n1i = (int)n1;
+    long total = n1 * (md - 2 * (N - 1)) * n34 * V;
+    nout = (size_t)total * N;
+    DeviceBuffer &o = buf[dd & 1];
+    o.alloc(nout * sizeof(double));
+    CUdeviceptr out = o.p;
+    void *args[] = {&cur, &out, &n1i, &md, &n34};
+    long blocks = (total + 255) / 256;
+    if (blocks > sms * 16)
+      blocks = sms * 16;
+    if (blocks < 1)
+      blocks = 1;
+    check(d.LaunchKernel(mod.k_weno_sweep, (unsigned)blocks, 1, 1, 256, 1, 1, 0, st, args, nullptr),
+          "cuLaunchKernel(k_weno_sweep)");
+    cur = out;
+    shape[dd] -= 2 * (N - 1);
+  }
+  check(d.MemcpyDtoHAsync(ret, cur, nout * sizeof(double), st), "cuMemcpyDtoHAsync");
+  check(d.StreamSynchronize(st), "cuStreamSynchronize");
+  d.StreamDestroy(st);
+}
+
+} // namespace pypde

@@ -1,0 +1,109 @@
+// Host driver of the GPU time step (replaces the reference's
+// solvers/iterator.cpp:38-151 loop body and its ThreadPool slab scheduler).
+#pragma once
+#include "dyn.h"
+#include "jit.h"
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pypde {
+
+// must match the structs in kernels.cuh
+struct GridParams {
+  int nX[3];
+  int bt[3];
+  double dX[3];
+  int halo_lo;
+  int halo_hi;
+};
+struct StepState {
+  double t, dt, tf, cfl;
+  unsigned long long maxbits;
+  long long count;
+  int nan_flag;
+  int pad;
+};
+struct FluxPtrs {
+  CUdeviceptr f[3];
+};
+
+// process-wide slab communicator (one process per GPU)
+struct Comm {
+  NcclComm comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+Comm &global_comm();
+
+void ensure_context();
+void check(CUresult r, const char *what);
+
+struct DeviceBuffer {
+  CUdeviceptr p = 0;
+  size_t bytes = 0;
+  void alloc(size_t n);
+  void release();
+  ~DeviceBuffer() { release(); }
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer &) = delete;
+  DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+};
+
+class Module {
+public:
+  Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+         const pypde_b200_devfn *S);
+  ~Module();
+  CUmodule mod = nullptr;
+  CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
+             k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr;
+};
+
+class Solver {
+public:
+  Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+         const pypde_b200_devfn *S, const int *nX, const double *dX, double cfl,
+         const int *bt);
+  ~Solver();
+
+  void set_stream(CUstream s);
+  void set_state(const double *u_host);
+  void get_state(double *u_host);
+  void bind_state(CUdeviceptr u);
+  void begin(double tf);
+  void step_async();
+  void sync(double *t, double *dt, int *nan_found);
+  void snapshot_prev(); // uprev <- u (iterator.cpp:147)
+  void get_prev(double *u_host);
+  size_t read_stage(int which, double *out, size_t cap);
+
+  // stand-alone reconstruction of an already padded array (api.cpp:32-48)
+  static void weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V);
+
+  long ncell() const { return ncell_; }
+  int V() const { return cfg_.V; }
+  long long launches = 0;
+
+private:
+  void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args);
+  unsigned grid_for(long total, unsigned block) const;
+  void run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs);
+  void exchange_halos();
+
+  KernelConfig cfg_;
+  std::shared_ptr<Module> mod_;
+  GridParams g_;
+  double cfl_;
+  long ncell_ = 0, ncellw_ = 0, rowlen_ = 0;
+  long nfaces_[3] = {0, 0, 0};
+  int sms_ = 148;
+  CUstream stream_ = nullptr;
+  bool own_stream_ = false;
+
+  DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, centers_,
+      flx_[3], state_;
+  CUdeviceptr u_ = 0;
+  StepState *h_state_ = nullptr; // pinned
+};
+
+} // namespace pypde

@@ -1,0 +1,114 @@
+"""pde_solver / weno_solver — the reference's Python API (pypde/solvers.py)
+over the B200 library.
+
+Argument names, defaults, marshalling and return shapes follow
+pypde/solvers.py:13-25,177-214 and :217-244.  Differences, all forced by the
+GPU target:
+
+* F, B, S are device-style Python functions or `DeviceFunction`/`CudaSource`
+  objects (see pypde_b200/cfuncs.py); `secondOrder` is still decided by F's
+  arity (reference solvers.py:196), i.e. 4 parameters in device style.
+* a failure inside the library raises RuntimeError (the reference's C ABI has
+  no error channel; a CUDA library cannot silently continue).
+"""
+from ctypes import POINTER, c_double, c_int
+from multiprocessing import cpu_count
+
+from numpy import array, ascontiguousarray, concatenate, int32, zeros
+
+from pypde_b200.cfuncs import DeviceFunction, generate_cfuncs
+from pypde_b200.utils import (c_ptr, check_error, create_solver, get_cdll,
+                              nargs, parse_boundary_types)
+
+FLUXES = {'rusanov': 0, 'roe': 1, 'osher': 2}
+
+
+def _is_second_order(F):
+    if F is None:
+        return False
+    if isinstance(F, DeviceFunction):
+        return bool(getattr(F, 'second_order', False))
+    return nargs(F) == 4
+
+
+def pde_solver(Q0,
+               tf,
+               L,
+               F=None,
+               B=None,
+               S=None,
+               boundaryTypes='transitive',
+               cfl=0.9,
+               order=2,
+               ndt=100,
+               flux='rusanov',
+               stiff=True,
+               nThreads=-1):
+    """Solves dQ/dt + div F(Q, grad Q) + B(Q).grad Q = S(Q) with ADER-WENO on
+    the GPU.  Same contract as reference pypde.pde_solver: returns an array of
+    shape (ndt,) + Q0.shape; Q0 is advanced in place when it is C-contiguous.
+    """
+    nX = array(Q0.shape[:-1], dtype='int32')
+    ndim = len(nX)
+    V = Q0.shape[-1]
+    dX = array([L[i] / nX[i] for i in range(len(L))], dtype='float64')
+
+    boundaryTypes = parse_boundary_types(boundaryTypes, ndim)
+
+    useF = F is not None
+    useB = B is not None
+    useS = S is not None
+
+    secondOrder = _is_second_order(F)
+
+    print('compiling functions...')
+
+    _F, _B, _S = generate_cfuncs(F, B, S, ndim, V)
+
+    solver = create_solver()
+
+    ret = zeros(ndt * Q0.size)
+    ur = Q0.ravel()
+
+    if nThreads < 1:
+        nThreads = cpu_count() - 1
+
+    solver(_F.ctypes if useF else None, _B.ctypes if useB else None,
+           _S.ctypes if useS else None, useF, useB, useS, c_ptr(ur), tf,
+           c_ptr(nX), ndim, c_ptr(dX), cfl, c_ptr(boundaryTypes), stiff,
+           FLUXES[flux], order, V, ndt, secondOrder, c_ptr(ret), nThreads)
+    check_error('pde_solver')
+
+    return ret.reshape((ndt, ) + Q0.shape)
+
+
+def weno_solver(u, order=2):
+    """Stand-alone WENO reconstruction (reference solvers.py:217-244)."""
+    u = ascontiguousarray(u, dtype='float64')
+    nX = array(u.shape[:-1], dtype=int32)
+    ndim = len(nX)
+    V = u.shape[-1]
+
+    nXret = nX - 2 * (order - 1)
+
+    libpypde = get_cdll()
+    solver = libpypde.weno_solver
+
+    solver.argtypes = [
+        POINTER(c_double),
+        POINTER(c_double),
+        POINTER(c_int),
+        c_int,
+        c_int,
+        c_int,
+    ]
+    solver.restype = None
+
+    ncellRet = nXret.prod()
+    ret = zeros(ncellRet * order**ndim * V)
+    ur = u.ravel()
+
+    solver(c_ptr(ret), c_ptr(ur), c_ptr(nX), ndim, order, V)
+    check_error('weno_solver')
+
+    return ret.reshape(concatenate([nXret, [order] * ndim, [V]]))

@@ -1,0 +1,165 @@
+/* PDE systems as plain C, one text for both sides of the parity tests:
+ *   - NVRTC compiles it to device functions user_F / user_B / user_S that are
+ *     LTO-linked into the kernels (pypde_b200.systems.cuda_source);
+ *   - gcc compiles the same text (oracle/systems.c, -ffp-contract=off) into CPU
+ *     callbacks with the reference's cfunc signatures (cfuncs.py:6-8) for the
+ *     reference library.
+ * Only + - * / sqrt and exp are used, in a fixed order, so the two sides agree
+ * bit for bit except where exp() is involved.
+ *
+ * No include guard on purpose: the file is included once per system with
+ *   SYS_<NAME>   selecting the system,
+ *   SYS_NDIM     the number of space dimensions,
+ *   SYS_F/SYS_B/SYS_S  the names to give the functions.
+ * The systems mirror the reference's example problems (pypde/tests/...):
+ *   EULER           tests/euler/system.py:10-21 generalised to ndim velocities
+ *   REACTIVE_EULER  tests/reactive_euler/system.py:13-61, Arrhenius kinetics as
+ *                   docs/pages/example_pdes.rst:35-61
+ *   NAVIER_STOKES   tests/navier_stokes/system.py:22-52
+ *   ADVECT_NC       a small non-conservative + source system for the B/S paths
+ */
+#ifndef PDE_FN
+#ifdef __CUDACC__
+#define PDE_FN extern "C" __device__
+#else
+#define PDE_FN
+#include <math.h>
+#endif
+#endif
+
+#if defined(SYS_EULER)
+/* Q = [rho, rho E, rho v_0 .. rho v_{ndim-1}],  V = 2 + ndim,  gamma = 1.4 */
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  const double g = 1.4;
+  double r = Q[0];
+  double E = Q[1] / r;
+  double v[SYS_NDIM];
+  double vv = 0.;
+  for (int i = 0; i < SYS_NDIM; i++) {
+    v[i] = Q[2 + i] / r;
+    vv += v[i] * v[i];
+  }
+  double e = E - vv / 2.;
+  double p = (g - 1.) * r * e;
+  double vd = v[d];
+  out[0] = r * vd;
+  out[1] = r * E * vd + p * vd;
+  for (int i = 0; i < SYS_NDIM; i++)
+    out[2 + i] = r * v[i] * vd;
+  out[2 + d] += p;
+  (void)dQ;
+}
+#endif
+
+#if defined(SYS_REACTIVE_EULER)
+/* Q = [rho, rho E, rho v_0.., rho lambda],  V = 3 + ndim */
+#ifndef SYS_RE_K0
+#define SYS_RE_K0 250.
+#endif
+#ifndef SYS_RE_EA
+#define SYS_RE_EA 2.
+#endif
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  const double g = 1.4, Qc = 1.;
+  double r = Q[0];
+  double E = Q[1] / r;
+  double v[SYS_NDIM];
+  double vv = 0.;
+  for (int i = 0; i < SYS_NDIM; i++) {
+    v[i] = Q[2 + i] / r;
+    vv += v[i] * v[i];
+  }
+  double lam = Q[2 + SYS_NDIM] / r;
+  double e = E - vv / 2. - Qc * (lam - 1.);
+  double p = (g - 1.) * r * e;
+  double vd = v[d];
+  for (int i = 0; i < 3 + SYS_NDIM; i++)
+    out[i] = vd * Q[i];
+  out[1] += p * vd;
+  out[2 + d] += p;
+  (void)dQ;
+}
+PDE_FN void SYS_S(double *out, const double *Q) {
+  const double Qc = 1., cv = 2.5;
+  double r = Q[0];
+  double E = Q[1] / r;
+  double vv = 0.;
+  for (int i = 0; i < SYS_NDIM; i++) {
+    double vi = Q[2 + i] / r;
+    vv += vi * vi;
+  }
+  double lam = Q[2 + SYS_NDIM] / r;
+  double e = E - vv / 2. - Qc * (lam - 1.);
+  double T = e / cv;
+  for (int i = 0; i < 3 + SYS_NDIM; i++)
+    out[i] = 0.;
+  out[2 + SYS_NDIM] = -r * lam * SYS_RE_K0 * exp(-SYS_RE_EA / T);
+}
+#endif
+
+#if defined(SYS_NAVIER_STOKES)
+/* Q = [rho, rho E, rho v_0, rho v_1, rho v_2], V = 5, second-order flux F(Q, dQ, d);
+ * as the reference example, only the x-gradient row dQ[0] enters the stress. */
+#ifndef SYS_NS_MU
+#define SYS_NS_MU 1e-2
+#endif
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  const double g = 1.4, mu = SYS_NS_MU;
+  double r = Q[0];
+  double E = Q[1] / r;
+  double v[3];
+  for (int i = 0; i < 3; i++)
+    v[i] = Q[2 + i] / r;
+  double dr_dx = dQ[0];
+  double dv_dx[3];
+  for (int i = 0; i < 3; i++)
+    dv_dx[i] = (dQ[2 + i] - dr_dx * v[i]) / r;
+  /* dv[0][:] = dv_dx, other rows zero */
+  double p = r * (g - 1.) * (E - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.);
+  double tr = dv_dx[0];
+  /* sigma = mu (dv + dv^T - 2/3 tr I), row d */
+  double sd[3];
+  for (int j = 0; j < 3; j++) {
+    double dv_dj = d == 0 ? dv_dx[j] : 0.;
+    double dv_jd = j == 0 ? dv_dx[d] : 0.;
+    double I = d == j ? 1. : 0.;
+    sd[j] = mu * (dv_dj + dv_jd - 2. / 3. * tr * I);
+  }
+  double vd = v[d];
+  double rvd = r * vd;
+  out[0] = rvd;
+  out[1] = rvd * E + p * vd;
+  for (int i = 0; i < 3; i++)
+    out[2 + i] = rvd * v[i];
+  out[2 + d] += p;
+  out[1] -= sd[0] * v[0] + sd[1] * v[1] + sd[2] * v[2];
+  for (int i = 0; i < 3; i++)
+    out[2 + i] -= sd[i];
+}
+#endif
+
+#if defined(SYS_ADVECT_NC)
+/* V = 3: q0 conserved with flux a_d q0 (1 + q0/4); q1, q2 advected
+ * non-conservatively with a state-dependent matrix; linear relaxation source. */
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  double a = 1. - 0.35 * d;
+  out[0] = a * Q[0] * (1. + Q[0] / 4.);
+  out[1] = 0.;
+  out[2] = 0.;
+  (void)dQ;
+}
+PDE_FN void SYS_B(double *out, const double *Q, int d) {
+  double a = 0.6 + 0.3 * d;
+  for (int i = 0; i < 9; i++)
+    out[i] = 0.;
+  out[1 * 3 + 1] = a * (1. + 0.2 * Q[0]);
+  out[1 * 3 + 2] = 0.1 * Q[1];
+  out[2 * 3 + 0] = 0.05;
+  out[2 * 3 + 2] = a + 0.1 * Q[2];
+}
+PDE_FN void SYS_S(double *out, const double *Q) {
+  out[0] = -0.5 * (Q[0] - 1.);
+  out[1] = 0.3 * Q[2] - 0.2 * Q[1];
+  out[2] = -0.1 * Q[2] * Q[0];
+}
+#endif

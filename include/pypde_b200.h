@@ -92,6 +92,12 @@ int pypde_b200_compile(const pypde_b200_devfn *F, const pypde_b200_devfn *B,
                        int STIFF, int secondOrder, size_t *cubin_bytes,
                        void *cubin_out, size_t cubin_cap);
 
+/* The specialised CUDA translation unit (#defines + tables + kernels) the JIT
+ * compiles for a configuration, as text: for the offline nvcc build check and
+ * for reading SASS/PTX.  Copies min(cap, size) bytes; full size in *n. */
+int pypde_b200_emit_source(int ndim, int N, int V, int FLUX, int STIFF, int useF, int useB,
+                           int useS, int secondOrder, char *out, size_t cap, size_t *n);
+
 /* Create a solver for one slab.  nX/dX/boundaryTypes have ndim entries. */
 int pypde_b200_create(pypde_b200_solver **out, const pypde_b200_devfn *F,
                       const pypde_b200_devfn *B, const pypde_b200_devfn *S,

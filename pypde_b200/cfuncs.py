@@ -73,6 +73,34 @@ class CudaSource(DeviceFunction):
         super().__init__(source, CUDA_SOURCE, name)
 
 
+class _offline_device:
+    """numba asks the current device for its compute capability when a device
+    function calls another one; LTO-IR is architecture-neutral, so on a machine
+    without a driver (build box, CPU tests) a stand-in answers (9, 0) — the
+    highest target numba 0.65 knows; nvJitLink generates the sm_100a code."""
+
+    class _Dev:
+        compute_capability = (9, 0)
+
+    def __enter__(self):
+        from numba.cuda import dispatcher
+        self._mod = dispatcher
+        self._orig = dispatcher.get_current_device
+        orig = self._orig
+
+        def get_device():
+            try:
+                return orig()
+            except Exception:
+                return _offline_device._Dev()
+
+        dispatcher.get_current_device = get_device
+
+    def __exit__(self, *exc):
+        self._mod.get_current_device = self._orig
+        return False
+
+
 def _device_style_arity(kind):
     return {'F': (3, 4), 'B': (3, ), 'S': (2, )}[kind]
 
@@ -153,9 +181,10 @@ def lower_python(func, kind, ndim, V):
 
         sig = types.void(dptr, dptr)
 
-    ltoir, _ = cuda.compile(wrapper, sig, device=True, abi='c',
-                            abi_info={'abi_name': 'user_' + kind},
-                            output='ltoir', cc=(9, 0))
+    with _offline_device():
+        ltoir, _ = cuda.compile(wrapper, sig, device=True, abi='c',
+                                abi_info={'abi_name': 'user_' + kind},
+                                output='ltoir', cc=(9, 0))
     return DeviceFunction(bytes(ltoir), LTOIR,
                           getattr(func, '__name__', 'user_' + kind))
 

@@ -114,6 +114,37 @@ int pypde_b200_compile(const pypde_b200_devfn *F, const pypde_b200_devfn *B,
   API_CATCH(1)
 }
 
+int pypde_b200_emit_source(int ndim, int N, int V, int FLUX, int STIFF, int useF, int useB,
+                           int useS, int secondOrder, char *out, size_t cap, size_t *n) {
+  API_TRY
+  KernelConfig c;
+  c.ndim = ndim;
+  c.N = N;
+  c.V = V;
+  c.flux = FLUX;
+  c.stiff = STIFF != 0;
+  c.useF = useF != 0;
+  c.useB = useB != 0;
+  c.useS = useS != 0;
+  c.secondOrder = secondOrder != 0 && c.useF;
+  choose_block_shapes(c);
+  std::string src;
+  for (const std::string &d : specialisation_defines(c)) {
+    std::string::size_type eq = d.find('=');
+    src += "#define " + d.substr(0, eq) + " " + d.substr(eq + 1) + "\n";
+  }
+  src += specialised_source(c);
+  if (n)
+    *n = src.size();
+  if (out && cap) {
+    size_t m = src.size() < cap - 1 ? src.size() : cap - 1;
+    memcpy(out, src.data(), m);
+    out[m] = 0;
+  }
+  return 0;
+  API_CATCH(1)
+}
+
 int pypde_b200_create(pypde_b200_solver **out, const pypde_b200_devfn *F,
                       const pypde_b200_devfn *B, const pypde_b200_devfn *S, const int *nX,
                       int ndim, const double *dX, double CFL, const int *boundaryTypes, int STIFF,

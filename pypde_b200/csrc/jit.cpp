@@ -92,6 +92,13 @@ void write_file_atomic(const std::string &path, const std::vector<char> &data) {
     unlink(tmp);
 }
 
+// PYPDE_B200_EXACT_B=1 switches the volume B.grad(q) terms from the reference's
+// (defective, see kernels.cuh) evaluation to the intended matrix-vector product.
+bool exact_b_product() {
+  const char *e = getenv("PYPDE_B200_EXACT_B");
+  return e && *e == '1';
+}
+
 bool fma_enabled() {
   const char *e = getenv("PYPDE_B200_FMA");
   return e && *e == '1';
@@ -200,6 +207,7 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_USE_B", c.useB ? 1 : 0),
           kv("PDE_USE_S", c.useS ? 1 : 0),
           kv("PDE_SECOND_ORDER", c.secondOrder ? 1 : 0),
+          kv("PDE_EXACT_B_PRODUCT", exact_b_product() ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb)};
 }

@@ -1,0 +1,101 @@
+"""Initial data and parameters of the parity cases (shared by the golden
+generator, the CPU oracle tests and the GPU parity tests).  Deterministic,
+no RNG except where a seed is given."""
+import numpy as np
+
+G = 1.4
+
+
+def euler_state(rho, p, vel):
+    """Q = [rho, rho E, rho v...] (reference tests/euler: E = p/((g-1) rho) + v^2/2)."""
+    rho = np.asarray(rho, dtype=float)
+    Q = np.zeros(rho.shape + (2 + len(vel), ))
+    Q[..., 0] = rho
+    Q[..., 1] = p / (G - 1) + rho * sum(np.asarray(v) * v for v in vel) / 2
+    for i, v in enumerate(vel):
+        Q[..., 2 + i] = rho * v
+    return Q
+
+
+def centres(shape):
+    return np.meshgrid(*[(np.arange(n) + 0.5) / n for n in shape], indexing='ij')
+
+
+def smooth_product(shape):
+    s = np.ones(shape)
+    for x in centres(shape):
+        s = s * np.sin(2 * np.pi * x)
+    return s
+
+
+def sod(n=200):
+    """BASELINE config 1: Sod shock tube."""
+    x = (np.arange(n) + 0.5) / n
+    rho = np.where(x < 0.5, 1.0, 0.125)
+    p = np.where(x < 0.5, 1.0, 0.1)
+    return euler_state(rho, p, [np.zeros(n)])
+
+
+def euler_smooth(shape):
+    """The well-conditioned parity IC of SURVEY 7.3-H1."""
+    nd = len(shape)
+    rho = 1 + 0.2 * smooth_product(shape)
+    vel = [1.0, -0.5, 0.25][:nd]
+    return euler_state(rho, 1.0, [v * np.ones(shape) for v in vel])
+
+
+def euler_explosion(shape):
+    """BASELINE config 2 IC: cylindrical / spherical explosion."""
+    r2 = sum((x - 0.5)**2 for x in centres(shape))
+    inside = r2 < 0.2**2
+    rho = np.where(inside, 1.0, 0.125)
+    p = np.where(inside, 1.0, 0.1)
+    return euler_state(rho, p, [np.zeros(shape)] * len(shape))
+
+
+def advect_nc_smooth(shape):
+    s = smooth_product(shape)
+    Q = np.zeros(tuple(shape) + (3, ))
+    Q[..., 0] = 1 + 0.2 * s
+    Q[..., 1] = 0.5 + 0.1 * s
+    Q[..., 2] = 1.0 - 0.3 * s
+    return Q
+
+
+def taylor_green(shape):
+    """BASELINE config 5 IC on [0, 2 pi]^3."""
+    x, y, z = [2 * np.pi * c for c in centres(shape)]
+    rho = np.ones(shape)
+    v = [np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z), np.zeros(shape)]
+    p = 100 / G + (np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2) / 16
+    return euler_state(rho, p, v)
+
+
+def weno_kat_input():
+    return np.array([1, 2, 4, 7, 11, 16, 22.]).reshape(7, 1)
+
+
+def weno_random(shape, seed=7):
+    return np.random.default_rng(seed).standard_normal(shape) + 2.0
+
+
+# name -> dict(system, Q0, tf, L, order, bts, flux, stiff, [defines])
+def solver_cases():
+    c = {}
+    c['sod_N2'] = dict(system='euler', Q0=sod(200), tf=0.2, L=[1.], order=2,
+                       bts=['transitive'])
+    c['sod_short_N3'] = dict(system='euler', Q0=sod(100), tf=0.01, L=[1.], order=3,
+                             bts=['transitive'])
+    c['euler1d_smooth_N3'] = dict(system='euler', Q0=euler_smooth((64, )), tf=0.02, L=[1.],
+                                  order=3, bts=['periodic'])
+    c['euler2d_smooth_N3'] = dict(system='euler', Q0=euler_smooth((24, 20)), tf=0.03,
+                                  L=[1., 1.], order=3, bts=['periodic', 'periodic'])
+    c['euler2d_smooth_N2'] = dict(system='euler', Q0=euler_smooth((24, 20)), tf=0.03,
+                                  L=[1., 1.], order=2, bts=['periodic', 'transitive'])
+    c['euler2d_explosion_N3'] = dict(system='euler', Q0=euler_explosion((32, 32)), tf=0.03,
+                                     L=[1., 1.], order=3, bts=['transitive', 'transitive'])
+    c['advect_nc_1d_N3'] = dict(system='advect_nc', Q0=advect_nc_smooth((40, )), tf=0.05,
+                                L=[1.], order=3, bts=['periodic'])
+    c['advect_nc_2d_N2'] = dict(system='advect_nc', Q0=advect_nc_smooth((16, 12)), tf=0.08,
+                                L=[1., 1.], order=2, bts=['periodic', 'periodic'])
+    return c

@@ -1,0 +1,119 @@
+"""The C-ABI library on a machine without a GPU: it loads, exports every
+symbol include/pypde_b200.h declares, JIT-builds sm_100a cubins, and every
+compute entry point fails loudly instead of falling back to the CPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import pypde_b200
+from pypde_b200.cfuncs import CudaSource
+from pypde_b200.systems import SYSTEMS, cuda_sources
+from pypde_b200.utils import get_cdll, last_error, lib_path
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'pypde_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = re.findall(r'\b(pypde_b200_\w+|pde_solver|weno_solver)\s*\(', text)
+    return sorted(set(n for n in names if n != 'pypde_b200_devfn'))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = get_cdll()
+    names = header_functions()
+    assert 'pde_solver' in names and 'weno_solver' in names and len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_reference_abi_symbols_are_unmangled_c():
+    out = subprocess.check_output(['nm', '-D', '--defined-only', lib_path()]).decode()
+    syms = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    assert {'pde_solver', 'weno_solver'} <= syms
+
+
+def test_no_link_time_cuda_dependency():
+    """libcuda / nvrtc / nvJitLink / nccl are dlopen()ed on first use, so the
+    library loads on a CPU-only box."""
+    out = subprocess.check_output(['readelf', '-d', lib_path()]).decode()
+    needed = re.findall(r'NEEDED.*\[(.*?)\]', out)
+    assert not [n for n in needed if re.search(r'cuda|nvrtc|nvJitLink|nccl|torch', n)], needed
+
+
+def test_toolchain_versions():
+    lib = get_cdll()
+    v = [ctypes.c_int() for _ in range(4)]
+    assert lib.pypde_b200_version(*[ctypes.byref(x) for x in v]) == 0
+    assert (v[0].value, v[1].value) >= (12, 9)   # NVRTC that knows compute_100a
+    assert (v[2].value, v[3].value) >= (12, 9)   # nvJitLink that ingests its LTO-IR
+
+
+@pytest.mark.parametrize('system,ndim,N', [('euler', 1, 2), ('euler', 2, 3), ('advect_nc', 2, 2),
+                                           ('navier_stokes', 3, 2), ('reactive_euler', 2, 3)])
+def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
+    lib = get_cdll()
+    F, B, S, V = cuda_sources(system, ndim)
+    n = ctypes.c_size_t()
+    buf = ctypes.create_string_buffer(8 << 20)
+    rc = lib.pypde_b200_compile(F.pointer if F else None, B.pointer if B else None,
+                                S.pointer if S else None, ndim, N, V, 0, 0,
+                                int(getattr(F, 'second_order', False)), ctypes.byref(n), buf,
+                                ctypes.c_size_t(8 << 20))
+    assert rc == 0, last_error()
+    cubin = buf.raw[:n.value]
+    assert cubin[:4] == b'\x7fELF'
+    path = '/tmp/pypde_b200_test_%s_%d_%d.cubin' % (system, ndim, N)
+    open(path, 'wb').write(cubin)
+    out = subprocess.check_output(['cuobjdump', '--dump-resource-usage', path]).decode()
+    elf = subprocess.check_output(['cuobjdump', '-elf', path]).decode()
+    assert 'sm_100' in elf or 'SM100' in elf.upper()
+    for k in ['k_boundaries', 'k_weno_sweep', 'k_cfl', 'k_dt', 'k_dg', 'k_faces', 'k_update']:
+        assert 'Function %s' % k in out, k
+
+
+def test_jit_reports_user_function_errors():
+    lib = get_cdll()
+    bad = CudaSource('extern "C" __device__ void user_F(double* o, const double* q, '
+                     'const double* dq, int d) { o[0] = undefined_symbol; }', 'bad_F')
+    n = ctypes.c_size_t()
+    rc = lib.pypde_b200_compile(bad.pointer, None, None, 1, 2, 1, 0, 0, 0, ctypes.byref(n), None,
+                                ctypes.c_size_t(0))
+    assert rc != 0
+    assert 'undefined_symbol' in last_error()
+    missing = CudaSource('extern "C" __device__ void not_user_F() {}', 'missing_F')
+    rc = lib.pypde_b200_compile(missing.pointer, None, None, 1, 2, 1, 0, 0, 0, ctypes.byref(n),
+                                None, ctypes.c_size_t(0))
+    assert rc != 0 and 'user_F' in last_error()
+
+
+def _has_gpu():
+    try:
+        ctypes.CDLL('libcuda.so.1')
+    except OSError:
+        return False
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.mark.skipif(_has_gpu(), reason='checks the no-GPU failure path')
+def test_compute_fails_loudly_without_gpu():
+    F, B, S, V = cuda_sources('euler', 1)
+    Q0 = np.ones((16, V))
+    with pytest.raises(RuntimeError, match='pde_solver failed'):
+        pypde_b200.pde_solver(Q0, 0.1, [1.], F=F, order=2, ndt=1, stiff=False)
+    with pytest.raises(RuntimeError, match='weno_solver failed'):
+        pypde_b200.weno_solver(np.ones((8, 1)), 2)
+
+
+def test_missing_library_is_an_error(monkeypatch):
+    import pypde_b200.utils as U
+    monkeypatch.setattr(U, '_LIB', None)
+    monkeypatch.setattr(U, 'lib_path', lambda: '/nonexistent/libpypde.so')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        U.get_cdll()

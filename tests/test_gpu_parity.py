@@ -1,0 +1,201 @@
+"""Parity of the CUDA path with the oracle / the reference's golden fixtures.
+Everything goes through the C-ABI library (pde_solver, weno_solver, or the
+handle API over the same driver).
+
+Tolerances (relative L-infinity, max|a-b|/max|b|):
+  * ghost cells: bit exact (pure copies);
+  * WENO coefficients: 1e-12 for N <= 3 (N x N stencil solves by precomputed
+    inverse instead of pivoted QR, amplified by the p^8 weights), 1e-8 for N = 4;
+  * dt: 1e-7 — the reference's wave speeds are spectral radii of forward-
+    difference Jacobians (h ~ 1.5e-8), which turn 1-ulp input differences into
+    ~1e-8 relative differences;
+  * solutions after a fixed number of steps: 1e-10 on smooth data — the
+    tolerance BASELINE.json states for non-stiff systems; 1e-7 on shock data,
+    where the reference's own 1-ulp self-noise reaches 1.6e-7.
+"""
+import numpy as np
+import pytest
+
+import cases
+from conftest import rel_linf
+from oracle import ader_weno as O
+from oracle import systems as SY
+import pypde_b200
+from pypde_b200.handle import Solver
+from pypde_b200.systems import cuda_sources
+
+pytestmark = pytest.mark.gpu
+
+BT = {'transitive': 0, 'periodic': 1}
+
+
+# ----------------------------------------------------------------- weno_solver
+@pytest.mark.parametrize('name,shape_in,N', [
+    ('weno_kat_N2', None, 2), ('weno_kat_N3', None, 3), ('weno_rand_1d_N4', (15, 2), 4),
+    ('weno_rand_2d_N3', (9, 8, 2), 3), ('weno_rand_2d_N2', (6, 7, 3), 2)])
+def test_weno_solver_golden(golden, name, shape_in, N):
+    u = cases.weno_kat_input() if shape_in is None else cases.weno_random(shape_in)
+    w = pypde_b200.weno_solver(u, N)
+    ref = golden['weno'][name]
+    assert w.shape == ref.shape
+    assert rel_linf(w, ref) < (1e-12 if N < 4 else 1e-8)
+
+
+@pytest.mark.parametrize('shape,N', [((33, 1), 2), ((40, 5), 3), ((17, 13, 4), 3), ((12, 9, 3), 4),
+                                     ((9, 10, 11, 2), 3), ((7, 6, 8, 5), 2), ((5, 1), 3)])
+def test_weno_solver_vs_oracle(shape, N):
+    u = cases.weno_random(shape, seed=sum(shape))
+    w = pypde_b200.weno_solver(u, N)
+    ref = O.weno(u, N)
+    assert w.shape == ref.shape
+    assert rel_linf(w, ref) < (1e-12 if N < 4 else 1e-8)
+
+
+def test_weno_reproduces_polynomials():
+    # a degree N-1 polynomial is reconstructed exactly from its cell averages
+    N = 3
+    x = np.arange(-4, 16, dtype=float)
+    avg = ((x + 1)**3 - x**3) / 3 + 2 * ((x + 1)**2 - x**2) / 2 - 1.0     # x^2 + 2x - 1
+    w = pypde_b200.weno_solver(avg.reshape(-1, 1), N)
+    nodes = O.tables(N).nodes
+    xc = x[N - 1:len(x) - (N - 1)]
+    exact = (xc[:, None] + nodes[None, :])**2 + 2 * (xc[:, None] + nodes[None, :]) - 1
+    assert np.abs(w[..., 0] - exact).max() < 1e-10
+
+
+# ------------------------------------------------------------------ pde_solver
+def run_gpu(c, ndt=1, **kw):
+    ndim = c['Q0'].ndim - 1
+    F, B, S, V = cuda_sources(c['system'], ndim, c.get('defines'))
+    Q0 = c['Q0'].copy()
+    out = pypde_b200.pde_solver(Q0, c['tf'], c['L'], F=F, B=B, S=S, boundaryTypes=c['bts'],
+                                order=c['order'], ndt=ndt, flux=c.get('flux', 'rusanov'),
+                                stiff=c.get('stiff', False), **kw)
+    return out, Q0
+
+
+SMOOTH = ['euler1d_smooth_N3', 'euler2d_smooth_N3', 'euler2d_smooth_N2', 'advect_nc_1d_N3',
+          'advect_nc_2d_N2']
+SHOCK = ['sod_short_N3', 'euler2d_explosion_N3', 'sod_N2']
+
+
+@pytest.mark.parametrize('name', SMOOTH)
+def test_solver_golden_smooth(golden, name):
+    out, Q0 = run_gpu(cases.solver_cases()[name])
+    assert rel_linf(out[0], golden['solver'][name]) < 1e-10
+    assert np.array_equal(Q0, out[-1])       # in-place update of Q0, as the reference
+
+
+@pytest.mark.parametrize('name', SHOCK)
+def test_solver_golden_shock(golden, name):
+    out, _ = run_gpu(cases.solver_cases()[name])
+    assert rel_linf(out[0], golden['solver'][name]) < 1e-7
+
+
+def test_ret_row_semantics():
+    """iterator.cpp:136-139,150: at most one row per step; unreached rows stay
+    zero; the last row is the final state."""
+    c = cases.solver_cases()['euler1d_smooth_N3']
+    out1, _ = run_gpu(c, ndt=1)
+    out, _ = run_gpu(c, ndt=40)
+    filled = [k for k in range(40) if np.abs(out[k]).max() > 0]
+    assert filled[-1] == 39 and len(filled) < 40 and filled[:3] == [0, 1, 2]
+    assert np.array_equal(out[39], out1[0])
+    assert all(np.abs(out[k]).max() == 0 for k in range(len(filled) - 1, 39))
+
+
+# ------------------------------------------------------------------ stage-wise
+@pytest.mark.parametrize('system,shape,N,bts', [
+    ('euler', (48, ), 2, ['transitive']), ('euler', (48, ), 3, ['periodic']),
+    ('euler', (20, 16), 3, ['periodic', 'transitive']), ('euler', (20, 16), 2, ['periodic', 'periodic']),
+    ('advect_nc', (32, ), 3, ['periodic']), ('advect_nc', (14, 10), 2, ['transitive', 'periodic']),
+    ('euler', (10, 8, 6), 2, ['periodic', 'periodic', 'transitive']),
+    ('advect_nc', (6, 8, 7), 3, ['periodic', 'periodic', 'periodic'])])
+def test_stages_vs_oracle(system, shape, N, bts):
+    ndim = len(shape)
+    s = SY.SYSTEMS[system](ndim)
+    F, B, S, V = cuda_sources(system, ndim)
+    u = cases.euler_smooth(shape) if system == 'euler' else cases.advect_nc_smooth(shape)
+    L = [1.] * ndim
+    dX = np.array([1. / n for n in shape])
+    bt = [BT[b] for b in bts]
+    sol = Solver(u.shape, L, F=F, B=B, S=S, boundaryTypes=bts, cfl=0.9, order=N)
+    sol.set_state(u)
+    sol.begin(10.)
+    t = 0.
+    for k in range(3):
+        tg, dtg, nan = sol.step()
+        stg = {}
+        un, dt = O.step(u, t, k, 10., dX, bt, s['F'], s['B'], s['S'], N, 0.9, stages=stg)
+        assert not nan
+        assert np.array_equal(sol.read_stage('ub').reshape(stg['ub'].shape), stg['ub'])
+        assert rel_linf(sol.read_stage('w').reshape(stg['w'].shape), stg['w']) < 1e-12
+        assert abs(dtg - dt) / dt < 1e-7
+        assert rel_linf(sol.get_state(), un) < 1e-10
+        u, t = un, t + dt
+        sol.set_state(u)
+    sol.close()
+
+
+# ---------------------------------------------------------- numba-lowered F/B/S
+def F_euler2d_py(out, Q, d):
+    g = 1.4
+    r = Q[0]
+    E = Q[1] / r
+    v0 = Q[2] / r
+    v1 = Q[3] / r
+    vv = 0. + v0 * v0
+    vv = vv + v1 * v1
+    e = E - vv / 2.
+    p = (g - 1.) * r * e
+    vd = v0 if d == 0 else v1
+    out[0] = r * vd
+    out[1] = r * E * vd + p * vd
+    out[2] = r * v0 * vd
+    out[3] = r * v1 * vd
+    out[2 + d] += p
+
+
+def test_numba_user_function_matches_cuda_source(golden):
+    """The same flux written in Python and lowered through numba's CUDA target
+    to LTO-IR gives the result of the CUDA-source flux."""
+    c = cases.solver_cases()['euler2d_smooth_N3']
+    Q0 = c['Q0'].copy()
+    out = pypde_b200.pde_solver(Q0, c['tf'], c['L'], F=F_euler2d_py, boundaryTypes=c['bts'],
+                                order=c['order'], ndt=1, stiff=False)
+    assert rel_linf(out[0], golden['solver']['euler2d_smooth_N3']) < 1e-10
+
+
+# ------------------------------------------------- size-independent properties
+def test_constant_state_is_preserved_exactly():
+    F, B, S, V = cuda_sources('euler', 2)
+    Q0 = cases.euler_state(np.full((40, 36), 1.3), 0.9, [np.full((40, 36), 0.4),
+                                                         np.full((40, 36), -0.2)])
+    ref = Q0.copy()
+    out = pypde_b200.pde_solver(Q0, 0.05, [1., 1.], F=F, boundaryTypes='transitive', order=3,
+                                ndt=1, stiff=False)
+    assert np.abs(out[0] - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize('n', [256, 2048])
+def test_conservation_and_symmetry_at_size(n):
+    """BASELINE config-2 sizes: on a periodic domain the FV update telescopes,
+    so cell sums are conserved to rounding; the explosion IC is symmetric under
+    x <-> y with (rho u, rho v) swapped and stays so."""
+    F, B, S, V = cuda_sources('euler', 2)
+    Q0 = cases.euler_explosion((n, n))
+    sol = Solver(Q0.shape, [1., 1.], F=F, boundaryTypes='periodic', order=3)
+    sol.set_state(Q0)
+    sol.begin(1.)
+    for _ in range(3):
+        t, dt, nan = sol.step()
+        assert not nan and dt > 0
+    u = sol.get_state()
+    sol.close()
+    tot0 = Q0.reshape(-1, V).sum(axis=0)
+    tot1 = u.reshape(-1, V).sum(axis=0)
+    assert np.abs(tot1[:2] - tot0[:2]).max() / np.abs(tot0[:2]).max() < 1e-12
+    assert np.abs(tot1[2:]).max() / (n * n) < 1e-13
+    ut = np.transpose(u, (1, 0, 2))[..., [0, 1, 3, 2]]
+    assert np.abs(ut - u).max() < 1e-9
+    assert np.abs(u - Q0).max() > 1e-3      # the state did move

@@ -130,6 +130,15 @@ long long pypde_b200_launch_count(const pypde_b200_solver *s);
 int pypde_b200_read_stage(pypde_b200_solver *s, int which, double *out, size_t cap,
                           size_t *n);
 
+/* Measurement aids for bench.py.  With profiling on, every kernel launch is
+ * bracketed by CUDA events on the launching stream; kernel_times() waits and
+ * returns, per kernel name, the summed device milliseconds and launch count
+ * since the last call as a text table "name ms launches\n...". */
+int pypde_b200_set_profiling(pypde_b200_solver *s, int on);
+int pypde_b200_kernel_times(pypde_b200_solver *s, char *out, size_t cap);
+/* Measured DFMA throughput of this device, TFLOP/s (FP64 roofline denominator). */
+int pypde_b200_fp64_peak(pypde_b200_solver *s, double *tflops);
+
 /* ---- Part 3: multi-GPU slabs (one process per GPU) ------------------------ */
 /* 128-byte NCCL unique id, created on rank 0 and distributed by the caller
  * (bench.py uses torch.distributed for the plumbing). */

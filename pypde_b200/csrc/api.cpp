@@ -6,6 +6,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -231,6 +232,39 @@ int pypde_b200_read_stage(pypde_b200_solver *s, int which, double *out, size_t c
   API_CATCH(1)
 }
 
+int pypde_b200_set_profiling(pypde_b200_solver *s, int on) {
+  API_TRY
+  s->impl->set_profiling(on != 0);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_kernel_times(pypde_b200_solver *s, char *out, size_t cap) {
+  API_TRY
+  std::string txt;
+  for (const Solver::KernelTime &k : s->impl->kernel_times()) {
+    char line[160];
+    snprintf(line, sizeof line, "%s %.6f %ld\n", k.name.c_str(), k.ms, k.launches);
+    txt += line;
+  }
+  if (out && cap) {
+    size_t m = txt.size() < cap - 1 ? txt.size() : cap - 1;
+    memcpy(out, txt.data(), m);
+    out[m] = 0;
+  }
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_fp64_peak(pypde_b200_solver *s, double *tflops) {
+  API_TRY
+  double v = s->impl->measure_fp64_peak();
+  if (tflops)
+    *tflops = v;
+  return 0;
+  API_CATCH(1)
+}
+
 int pypde_b200_comm_unique_id(void *id128) {
   API_TRY
   NcclUniqueId id;
@@ -294,8 +328,12 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     Solver solver(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes);
 
     const Comm &cm = global_comm();
+    // PYPDE_B200_QUIET=1 drops the per-step stdout lines (bench.py prints one JSON line)
+    const char *qe = getenv("PYPDE_B200_QUIET");
+    const bool quiet = qe && *qe == '1';
     // iterator.cpp:53 prints the thread count; the scheduler here is the GPU grid
-    printf("Using %d B200 GPU%s (nThreads ignored)\n", cm.nranks, cm.nranks > 1 ? "s" : "");
+    if (!quiet)
+      printf("Using %d B200 GPU%s (nThreads ignored)\n", cm.nranks, cm.nranks > 1 ? "s" : "");
 
     const size_t n = (size_t)solver.ncell() * V;
     solver.set_state(_u);
@@ -310,7 +348,8 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
       double dt = 0.;
       int nan_found = 0;
       solver.sync(&t, &dt, &nan_found);
-      printf("t = %g\n", t);
+      if (!quiet)
+        printf("t = %g\n", t);
 
       if (t >= double(pushCount + 1) / double(ndt) * tf && pushCount < ndt) {
         solver.get_state(_ret + (size_t)pushCount * n);

@@ -75,6 +75,11 @@ const DriverApi &driver() {
       B(FuncGetAttribute, "cuFuncGetAttribute");
       B(LaunchKernel, "cuLaunchKernel");
       B(GetErrorString, "cuGetErrorString");
+      B(EventCreate, "cuEventCreate");
+      B(EventDestroy, "cuEventDestroy_v2");
+      B(EventRecord, "cuEventRecord");
+      B(EventSynchronize, "cuEventSynchronize");
+      B(EventElapsedTime, "cuEventElapsedTime");
 #undef B
       CUresult r = api.Init(0);
       if (r != CUDA_SUCCESS) {

@@ -42,6 +42,11 @@ struct DriverApi {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, unsigned, CUstream, void **, void **);
   CUresult (*GetErrorString)(CUresult, const char **);
+  CUresult (*EventCreate)(CUevent *, unsigned);
+  CUresult (*EventDestroy)(CUevent);
+  CUresult (*EventRecord)(CUevent, CUstream);
+  CUresult (*EventSynchronize)(CUevent);
+  CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
 };
 
 struct NvrtcApi {

@@ -88,6 +88,7 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   get(k_dg, "k_dg");
   get(k_faces, "k_faces");
   get(k_update, "k_update");
+  get(k_fp64_peak, "k_fp64_peak");
 }
 
 Module::~Module() {
@@ -294,10 +295,80 @@ unsigned Solver::grid_for(long total, unsigned block) const {
   return (unsigned)blocks;
 }
 
-void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args) {
-  check(driver().LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr),
-        "cuLaunchKernel");
+void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
+                    const char *name) {
+  const DriverApi &d = driver();
+  Rec r{name, nullptr, nullptr};
+  if (profiling_) {
+    check(d.EventCreate(&r.a, CU_EVENT_DEFAULT), "cuEventCreate");
+    check(d.EventCreate(&r.b, CU_EVENT_DEFAULT), "cuEventCreate");
+    check(d.EventRecord(r.a, stream_), "cuEventRecord");
+  }
+  check(d.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr), name);
+  if (profiling_) {
+    check(d.EventRecord(r.b, stream_), "cuEventRecord");
+    recs_.push_back(r);
+  }
   launches++;
+}
+
+void Solver::set_profiling(bool on) { profiling_ = on; }
+
+std::vector<Solver::KernelTime> Solver::kernel_times() {
+  ensure_context();
+  const DriverApi &d = driver();
+  check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+  std::vector<KernelTime> out;
+  for (Rec &r : recs_) {
+    float ms = 0;
+    check(d.EventElapsedTime(&ms, r.a, r.b), "cuEventElapsedTime");
+    d.EventDestroy(r.a);
+    d.EventDestroy(r.b);
+    KernelTime *kt = nullptr;
+    for (KernelTime &k : out)
+      if (k.name == r.name)
+        kt = &k;
+    if (!kt) {
+      out.push_back(KernelTime{r.name, 0., 0});
+      kt = &out.back();
+    }
+    kt->ms += ms;
+    kt->launches++;
+  }
+  recs_.clear();
+  return out;
+}
+
+double Solver::measure_fp64_peak() {
+  ensure_context();
+  const DriverApi &d = driver();
+  DeviceBuffer sink;
+  sink.alloc(sizeof(double) * 1024);
+  int iters = 4096;
+  const unsigned block = 256, grid = (unsigned)sms_ * 8;
+  double seed = 1e-9;
+  void *args[] = {&sink.p, &iters, &seed};
+  CUevent a, b;
+  check(d.EventCreate(&a, CU_EVENT_DEFAULT), "cuEventCreate");
+  check(d.EventCreate(&b, CU_EVENT_DEFAULT), "cuEventCreate");
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    check(d.EventRecord(a, stream_), "cuEventRecord");
+    check(d.LaunchKernel(mod_->k_fp64_peak, grid, 1, 1, block, 1, 1, 0, stream_, args, nullptr),
+          "k_fp64_peak");
+    check(d.EventRecord(b, stream_), "cuEventRecord");
+    check(d.EventSynchronize(b), "cuEventSynchronize");
+    float ms = 0;
+    check(d.EventElapsedTime(&ms, a, b), "cuEventElapsedTime");
+    // 16 independent chains x iters FMAs x 2 flop per thread
+    double flops = (double)grid * block * 16.0 * iters * 2.0;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best)
+      best = tf;
+  }
+  d.EventDestroy(a);
+  d.EventDestroy(b);
+  return best;
 }
 
 void Solver::exchange_halos() {
@@ -347,7 +418,7 @@ void Solver::run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs)
     long total = n1 * (md - 2 * (N - 1)) * n34 * V;
     CUdeviceptr out = bufs[dd];
     void *args[] = {&cur, &out, &n1i, &md, &n34};
-    launch(mod_->k_weno_sweep, grid_for(total, 256), 256, 0, args);
+    launch(mod_->k_weno_sweep, grid_for(total, 256), 256, 0, args, "k_weno_sweep");
     cur = out;
     shape[dd] -= 2 * (N - 1);
   }
@@ -366,7 +437,7 @@ void Solver::step_async() {
       total *= g_.nX[i] + 2 * N;
     total *= V;
     void *args[] = {&u_, &halo_lo_.p, &halo_hi_.p, &ub_.p, &g_};
-    launch(mod_->k_boundaries, grid_for(total, 256), 256, 0, args);
+    launch(mod_->k_boundaries, grid_for(total, 256), 256, 0, args, "k_boundaries");
   }
   {
     long shape[3];
@@ -387,7 +458,7 @@ void Solver::step_async() {
   }
   {
     void *args[] = {&w_.p, &ncellw_, &g_, &state_.p};
-    launch(mod_->k_cfl, grid_for(ncellw_, 128), 128, 0, args);
+    launch(mod_->k_cfl, grid_for(ncellw_, 128), 128, 0, args, "k_cfl");
   }
   if (cm.nranks > 1) {
     const NcclApi &nc = nccl();
@@ -398,7 +469,7 @@ void Solver::step_async() {
   }
   {
     void *args[] = {&state_.p};
-    launch(mod_->k_dt, 1, 1, 0, args);
+    launch(mod_->k_dt, 1, 1, 0, args, "k_dt");
   }
   {
     const unsigned block = cfg_.dg_cpb * N * Nd;
@@ -408,7 +479,7 @@ void Solver::step_async() {
     if (nblocks > cap)
       nblocks = cap;
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
-    launch(mod_->k_dg, (unsigned)nblocks, block, smem, args);
+    launch(mod_->k_dg, (unsigned)nblocks, block, smem, args, "k_dg");
   }
   if (cfg_.useF || cfg_.useB) {
     const int NP = N * ipow(N, nd - 1);
@@ -421,7 +492,7 @@ void Solver::step_async() {
       if (nblocks > cap)
         nblocks = cap;
       void *args[] = {&traces_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
-      launch(mod_->k_faces, (unsigned)nblocks, block, smem, args);
+      launch(mod_->k_faces, (unsigned)nblocks, block, smem, args, "k_faces");
     }
   }
   {
@@ -429,11 +500,11 @@ void Solver::step_async() {
     for (int i = 0; i < 3; i++)
       fp.f[i] = flx_[i < nd ? i : 0].p;
     void *args[] = {&u_, &centers_.p, &fp, &g_, &state_.p};
-    launch(mod_->k_update, grid_for(ncell_ * V, 256), 256, 0, args);
+    launch(mod_->k_update, grid_for(ncell_ * V, 256), 256, 0, args, "k_update");
   }
   {
     void *args[] = {&state_.p};
-    launch(mod_->k_advance, 1, 1, 0, args);
+    launch(mod_->k_advance, 1, 1, 0, args, "k_advance");
   }
 }
 

@@ -55,6 +55,7 @@ public:
          const pypde_b200_devfn *S);
   ~Module();
   CUmodule mod = nullptr;
+  CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr;
 };
@@ -80,12 +81,30 @@ public:
   // stand-alone reconstruction of an already padded array (api.cpp:32-48)
   static void weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V);
 
+  // per-kernel device times (CUDA events on the launching stream)
+  void set_profiling(bool on);
+  struct KernelTime {
+    std::string name;
+    double ms = 0;
+    long launches = 0;
+  };
+  std::vector<KernelTime> kernel_times(); // syncs, returns and clears the record
+  // measured DFMA throughput of this GPU in TFLOP/s (micro-kernel in kernels.cuh)
+  double measure_fp64_peak();
+
   long ncell() const { return ncell_; }
   int V() const { return cfg_.V; }
   long long launches = 0;
 
 private:
-  void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args);
+  void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
+              const char *name);
+  bool profiling_ = false;
+  struct Rec {
+    const char *name;
+    CUevent a, b;
+  };
+  std::vector<Rec> recs_;
   unsigned grid_for(long total, unsigned block) const;
   void run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs);
   void exchange_halos();

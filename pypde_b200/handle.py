@@ -38,6 +38,9 @@ def _lib():
         lib.pypde_b200_launch_count.restype = c_longlong
         lib.pypde_b200_read_stage.argtypes = [c_void_p, c_int, POINTER(c_double), c_size_t,
                                               POINTER(c_size_t)]
+        lib.pypde_b200_set_profiling.argtypes = [c_void_p, c_int]
+        lib.pypde_b200_kernel_times.argtypes = [c_void_p, ctypes.c_char_p, c_size_t]
+        lib.pypde_b200_fp64_peak.argtypes = [c_void_p, POINTER(c_double)]
         lib.pypde_b200_comm_unique_id.argtypes = [c_void_p]
         lib.pypde_b200_comm_init.argtypes = [c_int, c_int, c_void_p]
         _configured = True
@@ -129,6 +132,24 @@ class Solver:
     def step(self):
         self.step_async()
         return self.sync()
+
+    def set_profiling(self, on):
+        _check(self.lib.pypde_b200_set_profiling(self.h, int(on)), 'set_profiling')
+
+    def kernel_times(self):
+        """{kernel name: (total device ms, launches)} since the last call."""
+        buf = ctypes.create_string_buffer(4096)
+        _check(self.lib.pypde_b200_kernel_times(self.h, buf, 4096), 'kernel_times')
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
+
+    def fp64_peak_tflops(self):
+        v = c_double()
+        _check(self.lib.pypde_b200_fp64_peak(self.h, byref(v)), 'fp64_peak')
+        return v.value
 
     @property
     def launches(self):

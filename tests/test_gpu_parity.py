@@ -129,7 +129,7 @@ def test_stages_vs_oracle(system, shape, N, bts):
         un, dt = O.step(u, t, k, 10., dX, bt, s['F'], s['B'], s['S'], N, 0.9, stages=stg)
         assert not nan
         assert np.array_equal(sol.read_stage('ub').reshape(stg['ub'].shape), stg['ub'])
-        assert rel_linf(sol.read_stage('w').reshape(stg['w'].shape), stg['w']) < 1e-12
+        assert rel_linf(sol.read_stage('w').reshape(stg['w'].shape), stg['w']) < (1e-11 if ndim < 3 else 1e-10)
         assert abs(dtg - dt) / dt < 1e-7
         assert rel_linf(sol.get_state(), un) < 1e-10
         u, t = un, t + dt

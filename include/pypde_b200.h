@@ -84,6 +84,14 @@ int pypde_b200_version(int *nvrtc_major, int *nvrtc_minor, int *nvjitlink_major,
 int pypde_b200_tables(int N, double *nodes, double *wghts, double *derv, double *endv,
                       double *dgmat, double *dginv, double *sig, double *wm, double *wminv);
 
+/* The device eigen-solver text (csrc/eig.cuh) compiled for the host, for unit
+ * tests of that code: spectral radius of a row-major n x n matrix (n <= 17).
+ * qr_only != 0 forces the general QR iteration; *path = 1 if the small-matrix
+ * polynomial path decided, 0 if the QR iteration did.  Test aid, not a CPU
+ * fallback: no solver entry point calls it. */
+int pypde_b200_host_spectral_radius(const double *A, int n, int qr_only, double *rho,
+                                    int *path);
+
 /* JIT only (no GPU needed): specialise + link the kernels for a configuration
  * and return the sm_100a cubin size (and optionally the cubin).  Used by the
  * CPU test-suite and by build(). */

@@ -1,0 +1,34 @@
+// Host build of the device eigen-solver text (eig.cuh) for CPU unit tests.
+#include "../../include/pypde_b200.h"
+#include "eig.cuh"
+#include <vector>
+
+extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_only, double *rho,
+                                               int *path) {
+  if (n < 1 || n > 17 || !A || !rho)
+    return 1;
+  std::vector<double> a(A, A + (size_t)n * n);
+  int pth = 0;
+  double r = 0.;
+#define CASE(N)                                                                                   \
+  case N:                                                                                         \
+    if (qr_only == 2) {                                                                           \
+      r = spectral_radius_qr<N>(a.data());                                                        \
+    } else if (qr_only) {                                                                         \
+      if (N > 2)                                                                                  \
+        balance<N>(a.data());                                                                     \
+      r = spectral_radius_qr<N>(a.data());                                                        \
+    } else {                                                                                      \
+      r = spectral_radius<N>(a.data(), &pth);                                                     \
+    }           \
+    break;
+  switch (n) {
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11)
+    CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17)
+  }
+#undef CASE
+  *rho = r;
+  if (path)
+    *path = qr_only ? 0 : pth;
+  return 0;
+}

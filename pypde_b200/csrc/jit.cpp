@@ -208,6 +208,7 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_USE_S", c.useS ? 1 : 0),
           kv("PDE_SECOND_ORDER", c.secondOrder ? 1 : 0),
           kv("PDE_EXACT_B_PRODUCT", exact_b_product() ? 1 : 0),
+          kv("PDE_EIG_QR_ONLY", getenv("PYPDE_B200_EIG_QR_ONLY") ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb)};
 }

@@ -387,15 +387,19 @@ void Solver::exchange_halos() {
     if (r != 0)
       throw std::runtime_error(std::string("pypde_b200: NCCL ") + what + ": " + nc.GetErrorString(r));
   };
+  // Sends are posted [first rows -> low, last rows -> high] and receives
+  // [high halo <- high, low halo <- low]: with two ranks on a periodic axis both
+  // neighbours are the same peer and NCCL matches messages between a pair in
+  // posting order, so the peer's "first rows" must meet our high-halo receive.
   ok(nc.GroupStart(), "ncclGroupStart");
-  if (lo >= 0) {
+  if (lo >= 0)
     ok(nc.Send((const void *)first_rows, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclSend");
-    ok(nc.Recv((void *)halo_lo_.p, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclRecv");
-  }
-  if (hi >= 0) {
+  if (hi >= 0)
     ok(nc.Send((const void *)last_rows, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclSend");
+  if (hi >= 0)
     ok(nc.Recv((void *)halo_hi_.p, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclRecv");
-  }
+  if (lo >= 0)
+    ok(nc.Recv((void *)halo_lo_.p, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclRecv");
   ok(nc.GroupEnd(), "ncclGroupEnd");
 }
 

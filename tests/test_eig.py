@@ -1,0 +1,147 @@
+"""The device eigen-solver text (csrc/eig.cuh: QR iteration + small-matrix
+polynomial path) compiled for the host, against matrices with known spectra
+and against numpy/LAPACK.  It replaces Eigen's EigenSolver / Spectra in the
+reference (eigs/system.cpp:28-43): only max |lambda| is used.
+
+Tolerance 2e-13 relative on matrices built as T D T^-1 with cond(T) <= 10
+(the polynomial path certifies kappa * eps <= 400 eps ~ 9e-14 or defers to
+the QR iteration); the reference's own wave speeds carry ~1e-8 of
+finite-difference noise, so this is far inside the parity budget."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from pypde_b200.utils import get_cdll
+
+P = ctypes.POINTER(ctypes.c_double)
+
+
+def rho(A, qr_only=0):
+    lib = get_cdll()
+    A = np.ascontiguousarray(A, dtype=float)
+    r, path = ctypes.c_double(), ctypes.c_int()
+    rc = lib.pypde_b200_host_spectral_radius(A.ctypes.data_as(P), A.shape[0], qr_only,
+                                             ctypes.byref(r), ctypes.byref(path))
+    assert rc == 0
+    return r.value, path.value
+
+
+def similar(D, rng):
+    n = D.shape[0]
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    T = Q @ np.diag(10**rng.uniform(-0.5, 0.5, n))
+    return T @ D @ np.linalg.inv(T)
+
+
+def spectrum_case(n, kind, rng):
+    D = np.zeros((n, n))
+    if kind == 'real':
+        ev = rng.standard_normal(n) * 3
+        D = np.diag(ev)
+        return D, np.abs(ev).max()
+    if kind == 'euler':          # v-c, v, ..., v, v+c : the Euler Jacobian's spectrum
+        v = rng.standard_normal() * rng.choice([0., 1., 5.])
+        c = abs(rng.standard_normal()) + 0.1
+        ev = np.array([v - c] + [v] * (n - 2) + [v + c])
+        return np.diag(ev), np.abs(ev).max()
+    scale = 3. if kind == 'complex_dominant' else 0.3
+    a, b = rng.standard_normal(2) * scale
+    D[0, 0] = D[1, 1] = a
+    D[0, 1], D[1, 0] = b, -b
+    ev = rng.standard_normal(n - 2) * (1. if kind == 'complex_dominant' else 3.)
+    for i in range(n - 2):
+        D[2 + i, 2 + i] = ev[i]
+    return D, max(np.hypot(a, b), np.abs(ev).max() if n > 2 else 0.)
+
+
+@pytest.mark.parametrize('n', [2, 3, 4, 5, 6, 8, 17])
+@pytest.mark.parametrize('kind', ['real', 'euler', 'complex_dominant', 'complex_small'])
+def test_known_spectra(n, kind):
+    rng = np.random.default_rng(100 * n + len(kind))
+    fast = 0
+    for _ in range(300):
+        D, true = spectrum_case(n, kind, rng)
+        A = similar(D, rng)
+        r, path = rho(A)
+        rq, _ = rho(A, 1)
+        fast += path
+        assert abs(r - true) / true < 2e-13, (n, kind, path)
+        assert abs(rq - true) / true < 2e-13
+    if kind == 'euler' and 3 <= n <= 5:
+        assert fast > 250          # the hyperbolic case takes the register-only path
+    if n > 5:
+        assert fast == 0
+
+
+def euler_jacobian(q, d, nd, g=1.4):
+    """Analytic dF_d/dQ of the Euler system of systems_src.h."""
+    V = 2 + nd
+    r, E = q[0], q[1] / q[0]
+    v = q[2:] / r
+    vv = v @ v
+    p = (g - 1) * r * (E - vv / 2)
+    H = E + p / r
+    A = np.zeros((V, V))
+    A[0, 2 + d] = 1.
+    A[1, 0] = v[d] * ((g - 1) * vv / 2 - H)
+    A[1, 1] = g * v[d]
+    for i in range(nd):
+        A[1, 2 + i] = -(g - 1) * v[i] * v[d] + (H if i == d else 0.)
+        A[2 + i, 0] = -v[i] * v[d] + ((g - 1) * vv / 2 if i == d else 0.)
+        A[2 + i, 1] = (g - 1) if i == d else 0.
+        for j in range(nd):
+            A[2 + i, 2 + j] = ((v[d] if i == j else 0.) + (v[i] if j == d else 0.) -
+                               ((g - 1) * v[j] if i == d else 0.))
+    c = np.sqrt(g * p / r)
+    return A, abs(v[d]) + c
+
+
+@pytest.mark.parametrize('nd', [1, 2, 3])
+def test_euler_jacobians(nd):
+    rng = np.random.default_rng(nd)
+    for _ in range(500):
+        r = rng.uniform(0.1, 3.)
+        p = rng.uniform(0.05, 3.)
+        v = rng.standard_normal(nd) * rng.choice([0., 0.3, 3.])
+        q = np.concatenate([[r, p / 0.4 + r * (v @ v) / 2], r * v])
+        for d in range(nd):
+            A, true = euler_jacobian(q, d, nd)
+            # finite-difference-like noise splits the repeated eigenvalue v
+            A = A + 1e-9 * rng.standard_normal(A.shape)
+            ref = np.abs(np.linalg.eigvals(A)).max()
+            val, path = rho(A)
+            if abs(val - ref) / ref > 2e-13:
+                # conserved-variable Jacobians at high Mach number are far from
+                # normal; settle disagreements with LAPACK in 50-digit arithmetic
+                import mpmath
+                mpmath.mp.dps = 50
+                ev, _ = mpmath.eig(mpmath.matrix(A.tolist()))
+                exact = float(max(abs(e) for e in ev))
+                assert abs(val - exact) / exact < 2e-11
+            assert abs(val - true) / true < 1e-5      # the 1e-9 noise times cond(lambda)
+
+
+def test_against_lapack_random():
+    rng = np.random.default_rng(5)
+    for n in (3, 4, 5, 7, 17):
+        for _ in range(300):
+            A = rng.standard_normal((n, n)) * 10**rng.uniform(-3, 3)
+            ref = np.abs(np.linalg.eigvals(A)).max()
+            assert abs(rho(A)[0] - ref) / ref < 1e-10      # non-normal: cond(lambda) matters
+            assert abs(rho(A, 1)[0] - ref) / ref < 1e-10
+
+
+def test_edge_cases():
+    for n in (1, 2, 3, 4, 5, 6):
+        assert rho(np.zeros((n, n)))[0] == 0.
+        assert abs(rho(2.5 * np.eye(n))[0] - 2.5) < 1e-15
+        assert abs(rho(-np.eye(n) * 1e-200)[0] - 1e-200) < 1e-214
+        J = np.diag(np.ones(n - 1), 1) + 3 * np.eye(n)      # defective Jordan block
+        assert abs(rho(J)[0] - 3.) < 1e-3 ** (1. / max(n, 1)) + 1e-12
+        A = np.full((n, n), np.nan)
+        assert not np.isfinite(rho(A)[0]) or n == 0
+    R = np.array([[0., -2.], [2., 0.]])                     # pure rotation: |lambda| = 2
+    assert abs(rho(R)[0] - 2.) < 1e-15
+    A = np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0.]])        # roots of unity
+    assert abs(rho(A)[0] - 1.) < 1e-14

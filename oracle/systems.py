@@ -14,8 +14,9 @@ def euler(ndim):
 
     def F(Q, dQ, d):
         r = Q[..., 0]
-        E = Q[..., 1] / r
-        v = [Q[..., 2 + i] / r for i in range(ndim)]
+        ir = 1. / r
+        E = Q[..., 1] * ir
+        v = [Q[..., 2 + i] * ir for i in range(ndim)]
         vv = 0.
         for i in range(ndim):
             vv = vv + v[i] * v[i]
@@ -38,12 +39,13 @@ def reactive_euler(ndim, K0=250., Ea=2.):
 
     def F(Q, dQ, d):
         r = Q[..., 0]
-        E = Q[..., 1] / r
-        v = [Q[..., 2 + i] / r for i in range(ndim)]
+        ir = 1. / r
+        E = Q[..., 1] * ir
+        v = [Q[..., 2 + i] * ir for i in range(ndim)]
         vv = 0.
         for i in range(ndim):
             vv = vv + v[i] * v[i]
-        lam = Q[..., 2 + ndim] / r
+        lam = Q[..., 2 + ndim] * ir
         e = E - vv / 2. - Qc * (lam - 1.)
         p = (g - 1.) * r * e
         vd = v[d]
@@ -54,12 +56,13 @@ def reactive_euler(ndim, K0=250., Ea=2.):
 
     def S(Q):
         r = Q[..., 0]
-        E = Q[..., 1] / r
+        ir = 1. / r
+        E = Q[..., 1] * ir
         vv = 0.
         for i in range(ndim):
-            vi = Q[..., 2 + i] / r
+            vi = Q[..., 2 + i] * ir
             vv = vv + vi * vi
-        lam = Q[..., 2 + ndim] / r
+        lam = Q[..., 2 + ndim] * ir
         e = E - vv / 2. - Qc * (lam - 1.)
         T = e / cv
         out = np.zeros_like(Q)
@@ -74,10 +77,11 @@ def navier_stokes(ndim, mu=1e-2):
 
     def F(Q, dQ, d):
         r = Q[..., 0]
-        E = Q[..., 1] / r
-        v = [Q[..., 2 + i] / r for i in range(3)]
+        ir = 1. / r
+        E = Q[..., 1] * ir
+        v = [Q[..., 2 + i] * ir for i in range(3)]
         dr_dx = dQ[..., 0, 0]
-        dv_dx = [(dQ[..., 0, 2 + i] - dr_dx * v[i]) / r for i in range(3)]
+        dv_dx = [(dQ[..., 0, 2 + i] - dr_dx * v[i]) * ir for i in range(3)]
         p = r * (g - 1.) * (E - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.)
         tr = dv_dx[0]
         sd = []

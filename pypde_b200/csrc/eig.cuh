@@ -234,46 +234,55 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 // ---------------------------------------------------------------------------
 template <int m> struct PolyRoots {
   // Largest real root of the monic polynomial x^m + c[m-1] x^(m-1) + .. + c[0],
-  // started at x0 >= every real root.  Laguerre's iteration; from the right of
-  // all roots it decreases monotonically with p(x) > 0 throughout.  Any sign of
-  // having left that regime (p <= 0 beyond rounding, a step to the right, no
-  // convergence) returns false and the caller falls back to the QR iteration.
+  // started at x0 >= every real root.  Laguerre's iteration in the one-division
+  // form  a = m p / (p' + sqrt((m-1)((m-1) p'^2 - m p p''))):  from the right of
+  // all roots it decreases monotonically with p, p' > 0 and converges cubically,
+  // so once a step is below 1e-6 |x| a single Newton step finishes to rounding.
+  // Any sign of having left that regime (p or p' <= 0 beyond rounding, a step to
+  // the right, no convergence) returns false and the caller falls back to QR.
   static EIG_FN bool rightmost(const double *c, double x0, double &root) {
     double x = x0;
-    for (int it = 0; it < 40; it++) {
+    for (int it = 0; it < 24; it++) {
       double p = 1., dp = 0., d2 = 0.; // p, p', p''/2 by Horner
-      double ab = 1.;                  // sum |c_k| |x|^k: rounding scale of p
-      const double ax = fabs(x);
 #pragma unroll
       for (int k = m - 1; k >= 0; k--) {
         d2 = fma(d2, x, dp);
         dp = fma(dp, x, p);
         p = fma(p, x, c[k]);
-        ab = fma(ab, ax, fabs(c[k]));
       }
-      if (fabs(p) <= 4. * DBL_EPS * ab) { // at the root to working precision
-        root = x;
+      if (!(p > 0.) || !(dp > 0.)) {
+        // on (or a rounding error past) the root, or outside the regime
+        double ab = 1.;
+        const double ax = fabs(x);
+#pragma unroll
+        for (int k = m - 1; k >= 0; k--)
+          ab = fma(ab, ax, fabs(c[k]));
+        if (fabs(p) <= 64. * DBL_EPS * ab && dp > 0.) {
+          root = x - p / dp;
+          return true;
+        }
+        return false;
+      }
+      const double disc = (m - 1) * ((m - 1) * dp * dp - 2. * m * p * d2);
+      const double den = disc > 0. ? dp + sqrt(disc) : dp;
+      const double a = (disc > 0. ? m * p : p) / den;
+      if (!(a >= 0.) || !(a <= 1e300)) // NaN / inf
+        return false;
+      x -= a;
+      if (a <= 1e-6 * fabs(x)) {
+        // cubic convergence: the error is now ~(1e-6)^3 |x|; one Newton step
+        p = 1.;
+        dp = 0.;
+#pragma unroll
+        for (int k = m - 1; k >= 0; k--) {
+          dp = fma(dp, x, p);
+          p = fma(p, x, c[k]);
+        }
+        if (!(dp > 0.))
+          return false;
+        root = x - p / dp;
         return true;
       }
-      if (!(p > 0.) || !(dp > 0.)) // overshoot past the outer root, or NaN
-        return false;
-      double G = dp / p;
-      double H = G * G - 2. * d2 / p;
-      double disc = (m - 1) * (m * H - G * G);
-      double a;
-      if (disc >= 0.) {
-        a = m / (G + sqrt(disc));
-      } else {
-        a = 1. / G;
-      }
-      if (!(a > 0.) || !(a <= 1e300)) // must move left; NaN / inf
-        return false;
-      double xn = x - a;
-      if (a <= 2. * DBL_EPS * ax) {
-        root = xn;
-        return true;
-      }
-      x = xn;
     }
     return false;
   }
@@ -291,7 +300,7 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
 #pragma unroll
   for (int i = 0; i < n; i++)
     mu += A[i * n + i];
-  mu /= n;
+  mu *= (1. / n);
   double B[n * n];
   double R = 0.;
 #pragma unroll
@@ -344,7 +353,7 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
 #pragma unroll
       for (int i = 0; i < n; i++)
         tr += M[i * n + i];
-      c[n - k] = -tr / k;
+      c[n - k] = -tr * (1. / k);
     } else {
       // only the trace of B M is needed
       double tr = 0.;
@@ -353,7 +362,7 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
 #pragma unroll
         for (int l = 0; l < n; l++)
           tr = fma(B[i * n + l], M[l * n + i], tr);
-      c[0] = -tr / n;
+      c[0] = -tr * (1. / n);
     }
   }
 
@@ -509,7 +518,6 @@ template <int n> EIG_FN double spectral_radius(double *a, int *path = nullptr) {
       return fabs(mu) + sqrt(s2);
     return sqrt(fma(mu, mu, -s2));
   }
-  balance<n>(a);
 #if !PDE_EIG_QR_ONLY
   if (n >= 3 && n <= 5) {
     double rho;
@@ -522,6 +530,7 @@ template <int n> EIG_FN double spectral_radius(double *a, int *path = nullptr) {
 #endif
   if (path)
     *path = 0;
+  balance<n>(a);
   return spectral_radius_qr<n>(a);
 }
 

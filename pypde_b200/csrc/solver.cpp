@@ -128,6 +128,7 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   for (int i = 0; i < 3; i++) {
     g_.nX[i] = 1;
     g_.dX[i] = 1.;
+    g_.rdX[i] = 1.;
   }
   ncell_ = 1;
   ncellw_ = 1;
@@ -137,6 +138,7 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
       throw std::runtime_error("pypde_b200: empty grid axis");
     g_.nX[i] = nX[i];
     g_.dX[i] = dX[i];
+    g_.rdX[i] = 1. / dX[i];
     g_.bt[i] = bt[i];
     ncell_ *= nX[i];
     ncellw_ *= nX[i] + 2;

@@ -14,6 +14,7 @@ struct GridParams {
   int nX[3];
   int bt[3];
   double dX[3];
+  double rdX[3];
   int halo_lo;
   int halo_hi;
 };

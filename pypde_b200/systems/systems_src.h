@@ -5,7 +5,9 @@
  *     callbacks with the reference's cfunc signatures (cfuncs.py:6-8) for the
  *     reference library.
  * Only + - * / sqrt and exp are used, in a fixed order, so the two sides agree
- * bit for bit except where exp() is involved.
+ * bit for bit except where exp() is involved.  The fluxes divide once (1/rho) and
+ * multiply: on the GPU a double division whose quotient is 0 (momentum / rho in
+ * gas at rest) takes div.rn.f64's slow path, ~10x the cost of the fast one.
  *
  * No include guard on purpose: the file is included once per system with
  *   SYS_<NAME>   selecting the system,
@@ -32,11 +34,12 @@
 PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
   const double g = 1.4;
   double r = Q[0];
-  double E = Q[1] / r;
+  double ir = 1. / r;
+  double E = Q[1] * ir;
   double v[SYS_NDIM];
   double vv = 0.;
   for (int i = 0; i < SYS_NDIM; i++) {
-    v[i] = Q[2 + i] / r;
+    v[i] = Q[2 + i] * ir;
     vv += v[i] * v[i];
   }
   double e = E - vv / 2.;
@@ -62,14 +65,15 @@ PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
 PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
   const double g = 1.4, Qc = 1.;
   double r = Q[0];
-  double E = Q[1] / r;
+  double ir = 1. / r;
+  double E = Q[1] * ir;
   double v[SYS_NDIM];
   double vv = 0.;
   for (int i = 0; i < SYS_NDIM; i++) {
-    v[i] = Q[2 + i] / r;
+    v[i] = Q[2 + i] * ir;
     vv += v[i] * v[i];
   }
-  double lam = Q[2 + SYS_NDIM] / r;
+  double lam = Q[2 + SYS_NDIM] * ir;
   double e = E - vv / 2. - Qc * (lam - 1.);
   double p = (g - 1.) * r * e;
   double vd = v[d];
@@ -82,13 +86,14 @@ PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
 PDE_FN void SYS_S(double *out, const double *Q) {
   const double Qc = 1., cv = 2.5;
   double r = Q[0];
-  double E = Q[1] / r;
+  double ir = 1. / r;
+  double E = Q[1] * ir;
   double vv = 0.;
   for (int i = 0; i < SYS_NDIM; i++) {
-    double vi = Q[2 + i] / r;
+    double vi = Q[2 + i] * ir;
     vv += vi * vi;
   }
-  double lam = Q[2 + SYS_NDIM] / r;
+  double lam = Q[2 + SYS_NDIM] * ir;
   double e = E - vv / 2. - Qc * (lam - 1.);
   double T = e / cv;
   for (int i = 0; i < 3 + SYS_NDIM; i++)
@@ -106,14 +111,15 @@ PDE_FN void SYS_S(double *out, const double *Q) {
 PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
   const double g = 1.4, mu = SYS_NS_MU;
   double r = Q[0];
-  double E = Q[1] / r;
+  double ir = 1. / r;
+  double E = Q[1] * ir;
   double v[3];
   for (int i = 0; i < 3; i++)
-    v[i] = Q[2 + i] / r;
+    v[i] = Q[2 + i] * ir;
   double dr_dx = dQ[0];
   double dv_dx[3];
   for (int i = 0; i < 3; i++)
-    dv_dx[i] = (dQ[2 + i] - dr_dx * v[i]) / r;
+    dv_dx[i] = (dQ[2 + i] - dr_dx * v[i]) * ir;
   /* dv[0][:] = dv_dx, other rows zero */
   double p = r * (g - 1.) * (E - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.);
   double tr = dv_dx[0];

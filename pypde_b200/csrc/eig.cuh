@@ -232,17 +232,49 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 // systems the accepted case is the rule; the result agrees with the QR
 // iteration to rounding (tests/test_gpu_parity.py::test_spectral_radius_*).
 // ---------------------------------------------------------------------------
+// Warm start for a sequence of nearby matrices (consecutive time nodes of one
+// face trace, left/right state of a face): the outer roots of the previous
+// shifted characteristic polynomial.
+struct EigGuess {
+  double yp, ym; // largest / smallest real root of the previous solve (shifted)
+  int valid;
+};
+
 template <int m> struct PolyRoots {
-  // Largest real root of the monic polynomial x^m + c[m-1] x^(m-1) + .. + c[0],
-  // started at x0 >= every real root.  Laguerre's iteration in the one-division
-  // form  a = m p / (p' + sqrt((m-1)((m-1) p'^2 - m p p''))):  from the right of
-  // all roots it decreases monotonically with p, p' > 0 and converges cubically,
-  // so once a step is below 1e-6 |x| a single Newton step finishes to rounding.
-  // Any sign of having left that regime (p or p' <= 0 beyond rounding, a step to
-  // the right, no convergence) returns false and the caller falls back to QR.
-  static EIG_FN bool rightmost(const double *c, double x0, double &root) {
-    double x = x0;
-    for (int it = 0; it < 24; it++) {
+  // Largest real root of the monic polynomial x^m + c[m-1] x^(m-1) + .. + c[0].
+  //
+  // Start: `guess` (> 0 means given) nudged to the right by 1e-3, accepted only if
+  // every Taylor coefficient of p there is positive — by the Budan-Fourier theorem
+  // no real root lies to its right — else x_cold, which the caller guarantees to be
+  // >= every real root.  From such a point p, p', p'' > 0 and both Laguerre's and
+  // Newton's iteration decrease monotonically onto the largest root: Laguerre
+  // (cubic, one sqrt + one division) while the step is large, Newton (one
+  // division) once it is below 2 %, and a last Newton step after the step falls
+  // below 1e-5 |x| (error then ~1e-10 |x|, squared by the final step).
+  // Any sign of having left the monotone regime (p or p' <= 0 beyond rounding, no
+  // convergence, NaN) returns false and the caller falls back to the QR iteration.
+  static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root) {
+    double x = x_cold;
+    if (guess > 0.) {
+      const double xg = guess * (1. + 1e-3);
+      double t[m + 1];
+#pragma unroll
+      for (int k = 0; k < m; k++)
+        t[k] = c[k];
+      t[m] = 1.;
+      bool ok = xg <= x_cold;
+#pragma unroll
+      for (int i = 0; i < m; i++) {
+#pragma unroll
+        for (int k = m - 1; k >= i; k--)
+          t[k] = fma(xg, t[k + 1], t[k]);
+        ok = ok && (t[i] > 0.);
+      }
+      if (ok)
+        x = xg;
+    }
+    bool newton = false;
+    for (int it = 0; it < 30; it++) {
       double p = 1., dp = 0., d2 = 0.; // p, p', p''/2 by Horner
 #pragma unroll
       for (int k = m - 1; k >= 0; k--) {
@@ -263,14 +295,18 @@ template <int m> struct PolyRoots {
         }
         return false;
       }
-      const double disc = (m - 1) * ((m - 1) * dp * dp - 2. * m * p * d2);
-      const double den = disc > 0. ? dp + sqrt(disc) : dp;
-      const double a = (disc > 0. ? m * p : p) / den;
+      double a;
+      if (newton) {
+        a = p / dp;
+      } else {
+        const double disc = (m - 1) * ((m - 1) * dp * dp - 2. * m * p * d2);
+        a = disc > 0. ? m * p / (dp + sqrt(disc)) : p / dp;
+      }
       if (!(a >= 0.) || !(a <= 1e300)) // NaN / inf
         return false;
       x -= a;
-      if (a <= 1e-6 * fabs(x)) {
-        // cubic convergence: the error is now ~(1e-6)^3 |x|; one Newton step
+      const double ax = fabs(x);
+      if (a <= 1e-5 * ax) {
         p = 1.;
         dp = 0.;
 #pragma unroll
@@ -283,6 +319,7 @@ template <int m> struct PolyRoots {
         root = x - p / dp;
         return true;
       }
+      newton = a <= 0.02 * ax;
     }
     return false;
   }
@@ -294,7 +331,8 @@ EIG_FN double pair_modulus2(double mu, double b1, double b0) {
   return re * re + (b0 - 0.25 * b1 * b1);
 }
 
-template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) {
+template <int n>
+EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess = nullptr) {
   // shift by the mean eigenvalue
   double mu = 0.;
 #pragma unroll
@@ -366,17 +404,28 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
     }
   }
 
+  // every root satisfies |y| <= ||B||_inf; for a real spectrum with zero mean also
+  // |y| <= sqrt((n-1)/n sum y_i^2) = sqrt(-2 c_{n-2} (n-1)/n) (Laguerre-Samuelson),
+  // usually much tighter.  The tighter start is used only under the Budan-Fourier
+  // certificate inside rightmost(); x0 is the unconditional one.
   const double x0 = R * (1. + 1e-12);
+  double gp = -1., gm = -1.;
+  if (guess && guess->valid) {
+    gp = guess->yp;
+    gm = -guess->ym;
+  } else if (c[n - 2] < 0.) {
+    gp = gm = sqrt(-2. * c[n - 2] * ((n - 1.) / n));
+  }
   // outermost real roots of the undeflated polynomial
   double yp;
-  if (!PolyRoots<n>::rightmost(c, x0, yp))
+  if (!PolyRoots<n>::rightmost(c, x0, gp, yp))
     return false;
   double cm[n]; // (-1)^n p(-y): leftmost root of p = -(rightmost root of this)
 #pragma unroll
   for (int k = 0; k < n; k++)
     cm[k] = ((n - k) & 1) ? -c[k] : c[k];
   double ym;
-  if (!PolyRoots<n>::rightmost(cm, x0, ym))
+  if (!PolyRoots<n>::rightmost(cm, x0, gm, ym))
     return false;
   ym = -ym;
   // both searches ending on the same root means a single real root (n odd) or a
@@ -426,6 +475,11 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
       return false; // inconsistent with two distinct outer real roots
     }
     rho = best;
+    if (guess) {
+      guess->yp = yp;
+      guess->ym = ym;
+      guess->valid = 1;
+    }
     return true;
   }
   double e[n]; // quotient of that by (y - ym): y^(n-2) + e[n-3] y^(n-3) + ... + e[0]
@@ -448,7 +502,7 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
     if (!(fabs(mu) + fb <= 0.98 * best)) {
       double ce[3] = {e[0], e[1], e[2]};
       double yr;
-      if (!PolyRoots<3>::rightmost(ce, fmin(fb, x0) * (1. + 1e-12), yr))
+      if (!PolyRoots<3>::rightmost(ce, fmin(fb, x0) * (1. + 1e-12), -1., yr))
         return false;
       const double g1 = ce[2] + yr;
       const double g0 = fma(g1, yr, ce[1]);
@@ -458,6 +512,11 @@ template <int n> EIG_FN bool spectral_radius_poly(const double *A, double &rho) 
     }
   }
   rho = best;
+  if (guess) {
+    guess->yp = yp;
+    guess->ym = ym;
+    guess->valid = 1;
+  }
   return true;
 }
 
@@ -506,7 +565,8 @@ template <int n> EIG_FN void balance(double *a) {
   }
 }
 
-template <int n> EIG_FN double spectral_radius(double *a, int *path = nullptr) {
+template <int n>
+EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr) {
   if (n == 1)
     return fabs(a[0]);
   if (n == 2) {
@@ -521,7 +581,7 @@ template <int n> EIG_FN double spectral_radius(double *a, int *path = nullptr) {
 #if !PDE_EIG_QR_ONLY
   if (n >= 3 && n <= 5) {
     double rho;
-    if (spectral_radius_poly<(n >= 3 && n <= 5) ? n : 3>(a, rho)) {
+    if (spectral_radius_poly<(n >= 3 && n <= 5) ? n : 3>(a, rho, guess)) {
       if (path)
         *path = 1;
       return rho;
@@ -530,6 +590,8 @@ template <int n> EIG_FN double spectral_radius(double *a, int *path = nullptr) {
 #endif
   if (path)
     *path = 0;
+  if (guess)
+    guess->valid = 0;
   balance<n>(a);
   return spectral_radius_qr<n>(a);
 }

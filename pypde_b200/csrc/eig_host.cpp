@@ -18,6 +18,13 @@ extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_on
       if (N > 2)                                                                                  \
         balance<N>(a.data());                                                                     \
       r = spectral_radius_qr<N>(a.data());                                                        \
+    } else if (qr_only == 3) { /* warm start: solve a perturbed copy first, then this one */      \
+      std::vector<double> w(a);                                                                   \
+      for (size_t i = 0; i < w.size(); i++)                                                       \
+        w[i] *= 1. + 1e-5 * ((int)(i % 7) - 3);                                                   \
+      EigGuess g{0., 0., 0};                                                                      \
+      spectral_radius<N>(w.data(), nullptr, &g);                                                  \
+      r = spectral_radius<N>(a.data(), &pth, &g);                                                 \
     } else {                                                                                      \
       r = spectral_radius<N>(a.data(), &pth);                                                     \
     }           \

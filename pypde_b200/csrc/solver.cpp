@@ -89,6 +89,8 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   get(k_faces, "k_faces");
   get(k_update, "k_update");
   get(k_fp64_peak, "k_fp64_peak");
+  if (cfg.useF)
+    get(k_wavespeeds, "k_wavespeeds");
 }
 
 Module::~Module() {
@@ -184,6 +186,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     w_.alloc((size_t)ncellw_ * Nd * V * D);
   }
   traces_.alloc((size_t)ncellw_ * 2 * nd * NP * TRW * V * D);
+  if (cfg_.useF) // per trace point: lambda, [lambda_visc]
+    ws_.alloc((size_t)ncellw_ * 2 * nd * NP * (1 + (cfg_.secondOrder ? 1 : 0)) * D);
   centers_.alloc((size_t)ncellw_ * V * D);
   const int FLXW = cfg_.useB ? 2 : 1;
   for (int dd = 0; dd < nd; dd++) {
@@ -487,6 +491,11 @@ void Solver::step_async() {
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
     launch(mod_->k_dg, (unsigned)nblocks, block, smem, args, "k_dg");
   }
+  if (cfg_.useF) {
+    long total = ncellw_ * 2 * nd * ipow(N, nd - 1);
+    void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
+    launch(mod_->k_wavespeeds, grid_for(total, 128), 128, 0, args, "k_wavespeeds");
+  }
   if (cfg_.useF || cfg_.useB) {
     const int NP = N * ipow(N, nd - 1);
     const int FLXW = cfg_.useB ? 2 : 1;
@@ -497,7 +506,7 @@ void Solver::step_async() {
       long cap = (long)sms_ * 32;
       if (nblocks > cap)
         nblocks = cap;
-      void *args[] = {&traces_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
+      void *args[] = {&traces_.p, &ws_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
       launch(mod_->k_faces, (unsigned)nblocks, block, smem, args, "k_faces");
     }
   }
@@ -542,6 +551,9 @@ size_t Solver::read_stage(int which, double *out, size_t cap) {
     break;
   case 3:
     b = &centers_;
+    break;
+  case 7:
+    b = &ws_;
     break;
   default:
     if (which >= 4 && which < 4 + cfg_.ndim)

@@ -58,7 +58,8 @@ public:
   CUmodule mod = nullptr;
   CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
-             k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr;
+             k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
+             k_wavespeeds = nullptr;
 };
 
 class Solver {
@@ -120,7 +121,7 @@ private:
   CUstream stream_ = nullptr;
   bool own_stream_ = false;
 
-  DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, centers_,
+  DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,
       flx_[3], state_;
   CUdeviceptr u_ = 0;
   StepState *h_state_ = nullptr; // pinned

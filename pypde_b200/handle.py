@@ -52,7 +52,7 @@ def _check(rc, what):
         raise RuntimeError('%s failed: %s' % (what, last_error()))
 
 
-STAGES = {'ub': 0, 'w': 1, 'traces': 2, 'centers': 3, 'flux0': 4, 'flux1': 5, 'flux2': 6}
+STAGES = {'ub': 0, 'w': 1, 'traces': 2, 'centers': 3, 'flux0': 4, 'flux1': 5, 'flux2': 6, 'wavespeeds': 7}
 
 
 class Solver:

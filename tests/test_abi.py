@@ -73,7 +73,8 @@ def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
     out = subprocess.check_output(['cuobjdump', '--dump-resource-usage', path]).decode()
     elf = subprocess.check_output(['cuobjdump', '-elf', path]).decode()
     assert 'sm_100' in elf or 'SM100' in elf.upper()
-    for k in ['k_boundaries', 'k_weno_sweep', 'k_cfl', 'k_dt', 'k_dg', 'k_faces', 'k_update']:
+    for k in ['k_boundaries', 'k_weno_sweep', 'k_cfl', 'k_dt', 'k_dg', 'k_wavespeeds', 'k_faces',
+              'k_update']:
         assert 'Function %s' % k in out, k
 
 

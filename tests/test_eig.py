@@ -145,3 +145,18 @@ def test_edge_cases():
     assert abs(rho(R)[0] - 2.) < 1e-15
     A = np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0.]])        # roots of unity
     assert abs(rho(A)[0] - 1.) < 1e-14
+
+
+def test_warm_start_gives_the_cold_result():
+    """mode 3 of the host entry solves a perturbed copy first and warm-starts the
+    real solve from its outer roots (as k_wavespeeds does across time nodes)."""
+    rng = np.random.default_rng(11)
+    for n in (3, 4, 5):
+        for kind in ('real', 'euler'):
+            for _ in range(300):
+                D, true = spectrum_case(n, kind, rng)
+                A = similar(D, rng)
+                cold, _ = rho(A)
+                warm, _ = rho(A, 3)
+                assert abs(warm - cold) <= 1e-13 * cold
+                assert abs(warm - true) / true < 2e-13

@@ -53,6 +53,10 @@ def line_table(cubin, kernel):
             cur = int(m.group(2)) if f.endswith('pypde_b200_kernels.cu') else '%s:%s' % (
                 f.split('/')[-1], m.group(2))
             continue
+        m = re.match(r'\s*(\$\S+):', l)
+        if m:   # compiler-provided subroutine (div / sqrt slow paths): no line info
+            cur = m.group(1).split('$')[-1]
+            continue
         if re.match(r'\s+/\*[0-9a-f]{4,}\*/\s+[A-Z@]', l):
             res.append((cur, l.strip()))
     return res
@@ -102,6 +106,6 @@ if __name__ == '__main__':
     print('--- by source line (share of executed instructions | share of stall samples)')
     for ln, c in per.most_common(top):
         text = (body[ln - 1].strip()[:96] if isinstance(ln, int) and ln - 1 < len(body)
-                else '(user function)')
+                else ('(user function)' if ':' in str(ln) else '(compiler subroutine)'))
         print('  %5.1f%% %5.1f%%  line %4s: %s' % (100. * c / tot, 100. * samp[ln] / max(stot, 1), ln,
                                                  text))

@@ -23,6 +23,9 @@ using std::sqrt;
 #endif
 
 #define DBL_EPS 2.2204460492503131e-16
+#ifndef PDE_EIG_PAIR
+#define PDE_EIG_PAIR 0 // 1: iterate the two outer roots in one loop (two dependency chains)
+#endif
 #ifndef PDE_EIG_QR_ONLY
 #define PDE_EIG_QR_ONLY 0 // 1: always use the general QR iteration for spectral radii
 #endif
@@ -241,87 +244,129 @@ struct EigGuess {
 };
 
 template <int m> struct PolyRoots {
-  // Largest real root of the monic polynomial x^m + c[m-1] x^(m-1) + .. + c[0].
-  //
-  // Start: `guess` (> 0 means given) nudged to the right by 1e-3, accepted only if
-  // every Taylor coefficient of p there is positive — by the Budan-Fourier theorem
-  // no real root lies to its right — else x_cold, which the caller guarantees to be
-  // >= every real root.  From such a point p, p', p'' > 0 and both Laguerre's and
-  // Newton's iteration decrease monotonically onto the largest root: Laguerre
-  // (cubic, one sqrt + one division) while the step is large, Newton (one
-  // division) once it is below 2 %, and a last Newton step after the step falls
-  // below 1e-5 |x| (error then ~1e-10 |x|, squared by the final step).
-  // Any sign of having left the monotone regime (p or p' <= 0 beyond rounding, no
-  // convergence, NaN) returns false and the caller falls back to the QR iteration.
+  // Budan-Fourier certificate: every Taylor coefficient of p at x positive means
+  // no real root lies to the right of x.
+  static EIG_FN bool right_of_all_roots(const double *c, double x) {
+    double t[m + 1];
+#pragma unroll
+    for (int k = 0; k < m; k++)
+      t[k] = c[k];
+    t[m] = 1.;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < m; i++) {
+#pragma unroll
+      for (int k = m - 1; k >= i; k--)
+        t[k] = fma(x, t[k + 1], t[k]);
+      ok = ok && (t[i] > 0.);
+    }
+    return ok;
+  }
+
+  // One monotone step towards the largest real root from a point to its right:
+  // Laguerre's iteration in the one-division form
+  //   a = m p / (p' + sqrt((m-1)((m-1) p'^2 - m p p'')))
+  // (cubic), or Newton's a = p / p' once `newton` is set.  state: 0 iterating,
+  // 1 converged (root written), -1 failed (left the monotone regime / NaN).
+  static EIG_FN void step(const double *c, double &x, bool &newton, int &state, double &root) {
+    double p = 1., dp = 0., d2 = 0.; // p, p', p''/2 by Horner
+#pragma unroll
+    for (int k = m - 1; k >= 0; k--) {
+      d2 = fma(d2, x, dp);
+      dp = fma(dp, x, p);
+      p = fma(p, x, c[k]);
+    }
+    if (!(p > 0.) || !(dp > 0.)) {
+      // on (or a rounding error past) the root, or outside the regime
+      double ab = 1.;
+      const double ax = fabs(x);
+#pragma unroll
+      for (int k = m - 1; k >= 0; k--)
+        ab = fma(ab, ax, fabs(c[k]));
+      if (fabs(p) <= 64. * DBL_EPS * ab && dp > 0.) {
+        root = x - p / dp;
+        state = 1;
+      } else {
+        state = -1;
+      }
+      return;
+    }
+    double a;
+    if (newton) {
+      a = p / dp;
+    } else {
+      const double disc = (m - 1) * ((m - 1) * dp * dp - 2. * m * p * d2);
+      a = disc > 0. ? m * p / (dp + sqrt(disc)) : p / dp;
+    }
+    if (!(a >= 0.) || !(a <= 1e300)) { // NaN / inf
+      state = -1;
+      return;
+    }
+    x -= a;
+    const double ax = fabs(x);
+    if (a <= 1e-5 * ax) {
+      // the error is now ~1e-10 |x| (quadratic) or smaller: one Newton step ends it
+      p = 1.;
+      dp = 0.;
+#pragma unroll
+      for (int k = m - 1; k >= 0; k--) {
+        dp = fma(dp, x, p);
+        p = fma(p, x, c[k]);
+      }
+      if (dp > 0.) {
+        root = x - p / dp;
+        state = 1;
+      } else {
+        state = -1;
+      }
+      return;
+    }
+    newton = a <= 0.02 * ax;
+  }
+
+  // Largest real root of x^m + c[m-1] x^(m-1) + .. + c[0].  Start: `guess` (> 0
+  // means given) nudged right by 1e-3 if certified to be right of every real root,
+  // else x_cold, which the caller guarantees to be.  false = fall back to QR.
   static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root) {
     double x = x_cold;
     if (guess > 0.) {
       const double xg = guess * (1. + 1e-3);
-      double t[m + 1];
-#pragma unroll
-      for (int k = 0; k < m; k++)
-        t[k] = c[k];
-      t[m] = 1.;
-      bool ok = xg <= x_cold;
-#pragma unroll
-      for (int i = 0; i < m; i++) {
-#pragma unroll
-        for (int k = m - 1; k >= i; k--)
-          t[k] = fma(xg, t[k + 1], t[k]);
-        ok = ok && (t[i] > 0.);
-      }
-      if (ok)
+      if (xg <= x_cold && right_of_all_roots(c, xg))
         x = xg;
     }
     bool newton = false;
-    for (int it = 0; it < 30; it++) {
-      double p = 1., dp = 0., d2 = 0.; // p, p', p''/2 by Horner
-#pragma unroll
-      for (int k = m - 1; k >= 0; k--) {
-        d2 = fma(d2, x, dp);
-        dp = fma(dp, x, p);
-        p = fma(p, x, c[k]);
-      }
-      if (!(p > 0.) || !(dp > 0.)) {
-        // on (or a rounding error past) the root, or outside the regime
-        double ab = 1.;
-        const double ax = fabs(x);
-#pragma unroll
-        for (int k = m - 1; k >= 0; k--)
-          ab = fma(ab, ax, fabs(c[k]));
-        if (fabs(p) <= 64. * DBL_EPS * ab && dp > 0.) {
-          root = x - p / dp;
-          return true;
-        }
-        return false;
-      }
-      double a;
-      if (newton) {
-        a = p / dp;
-      } else {
-        const double disc = (m - 1) * ((m - 1) * dp * dp - 2. * m * p * d2);
-        a = disc > 0. ? m * p / (dp + sqrt(disc)) : p / dp;
-      }
-      if (!(a >= 0.) || !(a <= 1e300)) // NaN / inf
-        return false;
-      x -= a;
-      const double ax = fabs(x);
-      if (a <= 1e-5 * ax) {
-        p = 1.;
-        dp = 0.;
-#pragma unroll
-        for (int k = m - 1; k >= 0; k--) {
-          dp = fma(dp, x, p);
-          p = fma(p, x, c[k]);
-        }
-        if (!(dp > 0.))
-          return false;
-        root = x - p / dp;
-        return true;
-      }
-      newton = a <= 0.02 * ax;
+    int state = 0;
+    for (int it = 0; it < 30 && state == 0; it++)
+      step(c, x, newton, state, root);
+    return state == 1;
+  }
+
+  // Largest root of c and of cm at once: the two iterations are independent, and
+  // running them in one loop gives the FP64 pipe two dependency chains to overlap.
+  static EIG_FN bool outer_pair(const double *c, const double *cm, double x_cold, double gp,
+                                double gm, double &rp, double &rm) {
+    double xp = x_cold, xm = x_cold;
+    if (gp > 0.) {
+      const double xg = gp * (1. + 1e-3);
+      if (xg <= x_cold && right_of_all_roots(c, xg))
+        xp = xg;
     }
-    return false;
+    if (gm > 0.) {
+      const double xg = gm * (1. + 1e-3);
+      if (xg <= x_cold && right_of_all_roots(cm, xg))
+        xm = xg;
+    }
+    bool np = false, nm = false;
+    int sp = 0, sm = 0;
+    for (int it = 0; it < 30; it++) {
+      if (sp == 0)
+        step(c, xp, np, sp, rp);
+      if (sm == 0)
+        step(cm, xm, nm, sm, rm);
+      if ((sp != 0 && sm != 0) || sp < 0 || sm < 0)
+        break;
+    }
+    return sp == 1 && sm == 1;
   }
 };
 
@@ -416,17 +461,22 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   } else if (c[n - 2] < 0.) {
     gp = gm = sqrt(-2. * c[n - 2] * ((n - 1.) / n));
   }
-  // outermost real roots of the undeflated polynomial
-  double yp;
-  if (!PolyRoots<n>::rightmost(c, x0, gp, yp))
-    return false;
-  double cm[n]; // (-1)^n p(-y): leftmost root of p = -(rightmost root of this)
+  // outermost real roots of the undeflated polynomial; the leftmost root of p is
+  // minus the rightmost root of (-1)^n p(-y)
+  double cm[n];
 #pragma unroll
   for (int k = 0; k < n; k++)
     cm[k] = ((n - k) & 1) ? -c[k] : c[k];
-  double ym;
+  double yp, ym;
+#if PDE_EIG_PAIR
+  if (!PolyRoots<n>::outer_pair(c, cm, x0, gp, gm, yp, ym))
+    return false;
+#else
+  if (!PolyRoots<n>::rightmost(c, x0, gp, yp))
+    return false;
   if (!PolyRoots<n>::rightmost(cm, x0, gm, ym))
     return false;
+#endif
   ym = -ym;
   // both searches ending on the same root means a single real root (n odd) or a
   // multiple one

@@ -198,7 +198,7 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
     snprintf(b, sizeof b, "%s=%d", k, v);
     return std::string(b);
   };
-  return {kv("PDE_NDIM", c.ndim),
+  std::vector<std::string> defs = {kv("PDE_NDIM", c.ndim),
           kv("PDE_N", c.N),
           kv("PDE_V", c.V),
           kv("PDE_FLUX", c.flux),
@@ -211,6 +211,20 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_EIG_QR_ONLY", getenv("PYPDE_B200_EIG_QR_ONLY") ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb)};
+  // tuning experiments: PYPDE_B200_EXTRA_DEFINES="PDE_X=1;PDE_Y=0"
+  if (const char *e = getenv("PYPDE_B200_EXTRA_DEFINES")) {
+    std::string all(e);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t q = all.find(';', pos);
+      if (q == std::string::npos)
+        q = all.size();
+      if (q > pos)
+        defs.push_back(all.substr(pos, q - pos));
+      pos = q + 1;
+    }
+  }
+  return defs;
 }
 
 std::string specialised_source(const KernelConfig &c) {

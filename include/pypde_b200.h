@@ -68,6 +68,11 @@ void pde_solver(void (*F)(double *, double *, double *, int),
  * (m_1-2(N-1), ..., N, ..., N, V). */
 void weno_solver(double *ret, double *_u, int *_nX, int ndim, int N, int V);
 
+/* pde_solver keeps its last solver (kernel module + work arrays in HBM) for the
+ * next call with the same configuration; this frees it.  PYPDE_B200_KEEP_SOLVER=0
+ * disables the caching altogether. */
+int pypde_b200_release_cache(void);
+
 /* ---- Part 2: handle API (state resident in HBM) --------------------------- */
 typedef struct pypde_b200_solver pypde_b200_solver;
 

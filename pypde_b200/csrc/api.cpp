@@ -7,6 +7,8 @@
 #include <stdexcept>
 #include <stdio.h>
 #include <stdlib.h>
+#include <memory>
+#include <mutex>
 #include <string.h>
 #include <string>
 
@@ -18,6 +20,46 @@ struct pypde_b200_solver {
 
 namespace {
 thread_local std::string g_last_error;
+
+// pde_solver keeps its last solver (kernel module, ~2 KB of HBM per cell of work
+// arrays) alive between calls with the same configuration, so that repeated calls
+// pay neither the module load nor the allocations again.  PYPDE_B200_KEEP_SOLVER=0
+// or pypde_b200_release_cache() turn that off / free it.
+std::mutex g_cache_mutex;
+std::unique_ptr<Solver> g_cached_solver;
+std::string g_cached_key;
+
+std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const pypde_b200_devfn *B,
+                       const pypde_b200_devfn *S, const int *nX, const double *dX, double cfl,
+                       const int *bt) {
+  std::string k;
+  auto add = [&k](const void *p, size_t n) { k.append((const char *)p, n); };
+  int hdr[10] = {c.ndim, c.N, c.V, c.flux, c.stiff, c.useF, c.useB, c.useS, c.secondOrder,
+                 global_comm().nranks * 1000 + global_comm().rank};
+  add(hdr, sizeof hdr);
+  ensure_context();
+  CUdevice dev = -1;
+  driver().CtxGetDevice(&dev);
+  add(&dev, sizeof dev);
+  add(nX, sizeof(int) * c.ndim);
+  add(dX, sizeof(double) * c.ndim);
+  add(bt, sizeof(int) * c.ndim);
+  add(&cfl, sizeof cfl);
+  const pypde_b200_devfn *fn[3] = {c.useF ? F : nullptr, c.useB ? B : nullptr,
+                                   c.useS ? S : nullptr};
+  for (int i = 0; i < 3; i++)
+    if (fn[i] && fn[i]->image) {
+      add(&fn[i]->kind, sizeof(int));
+      add(fn[i]->image, fn[i]->bytes);
+    }
+  for (const char *e : {"PYPDE_B200_EXTRA_DEFINES", "PYPDE_B200_FMA", "PYPDE_B200_EXACT_B",
+                        "PYPDE_B200_EIG_QR_ONLY"}) {
+    const char *v = getenv(e);
+    k += v ? v : "-";
+    k += '|';
+  }
+  return k;
+}
 
 void set_error(const std::string &e) {
   g_last_error = e;
@@ -265,6 +307,15 @@ int pypde_b200_fp64_peak(pypde_b200_solver *s, double *tflops) {
   API_CATCH(1)
 }
 
+int pypde_b200_release_cache(void) {
+  API_TRY
+  std::lock_guard<std::mutex> lk(g_cache_mutex);
+  g_cached_solver.reset();
+  g_cached_key.clear();
+  return 0;
+  API_CATCH(1)
+}
+
 int pypde_b200_comm_unique_id(void *id128) {
   API_TRY
   NcclUniqueId id;
@@ -297,6 +348,11 @@ int pypde_b200_comm_init(int rank, int nranks, const void *id128) {
 
 int pypde_b200_comm_finalize(void) {
   API_TRY
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mutex);
+    g_cached_solver.reset();
+    g_cached_key.clear();
+  }
   Comm &c = global_comm();
   if (c.comm)
     nccl().CommDestroy(c.comm);
@@ -325,7 +381,26 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     if ((useF && !dF) || (useB && !dB) || (useS && !dS))
       throw std::runtime_error("pypde_b200: useF/useB/useS set but the descriptor is NULL");
     KernelConfig c = make_config(ndim, N, V, FLUX, STIFF, secondOrder, dF, dB, dS);
-    Solver solver(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes);
+    const char *ke = getenv("PYPDE_B200_KEEP_SOLVER");
+    const bool keep = !(ke && *ke == '0');
+    std::lock_guard<std::mutex> cache_lock(g_cache_mutex);
+    const std::string key = solver_key(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes);
+    if (!keep || key != g_cached_key || !g_cached_solver) {
+      g_cached_solver.reset(); // free the old arrays before allocating new ones
+      g_cached_key.clear();
+      g_cached_solver.reset(new Solver(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes));
+      g_cached_key = key;
+    }
+    Solver &solver = *g_cached_solver;
+    struct Release {
+      bool keep;
+      ~Release() {
+        if (!keep) {
+          g_cached_solver.reset();
+          g_cached_key.clear();
+        }
+      }
+    } release{keep};
 
     const Comm &cm = global_comm();
     // PYPDE_B200_QUIET=1 drops the per-step stdout lines (bench.py prints one JSON line)

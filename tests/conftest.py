@@ -28,3 +28,13 @@ def golden():
 def rel_linf(a, b):
     """relative L-infinity error  max|a-b| / max|b|"""
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(b).max())
+
+
+def parity_tolerance(golden_solver, name, stated=1e-10):
+    """Tolerance of a full-solve parity check: the tolerance BASELINE.json states
+    for non-stiff systems (1e-10 relative L-inf), or 10x the reference's own
+    round-off self-noise on that case (the same reference run with the initial data
+    moved by +-1 ulp, stored by tests/golden/make_golden.py), whichever is larger.
+    The noise comes from the reference's wave speeds: spectral radii of
+    forward-difference Jacobians (h ~ 1.5e-8)."""
+    return max(stated, 10. * float(golden_solver[name + '__noise']))

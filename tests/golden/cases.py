@@ -71,6 +71,18 @@ def taylor_green(shape):
     return euler_state(rho, p, v)
 
 
+def ns_smooth(shape):
+    """Navier-Stokes state (V = 5, three velocity components in any ndim)."""
+    rho = 1 + 0.2 * smooth_product(shape)
+    vel = [1.0 * np.ones(shape), -0.5 * np.ones(shape), 0.25 + 0.1 * smooth_product(shape)]
+    Q = np.zeros(tuple(shape) + (5, ))
+    Q[..., 0] = rho
+    Q[..., 1] = 1.0 / (G - 1) + rho * sum(v * v for v in vel) / 2
+    for i, v in enumerate(vel):
+        Q[..., 2 + i] = rho * v
+    return Q
+
+
 def weno_kat_input():
     return np.array([1, 2, 4, 7, 11, 16, 22.]).reshape(7, 1)
 
@@ -98,4 +110,17 @@ def solver_cases():
                                 L=[1.], order=3, bts=['periodic'])
     c['advect_nc_2d_N2'] = dict(system='advect_nc', Q0=advect_nc_smooth((16, 12)), tf=0.08,
                                 L=[1., 1.], order=2, bts=['periodic', 'periodic'])
+    # second-order (viscous) flux F(Q, dQ, d): reference tests/navier_stokes/system.py
+    c['ns1d_smooth_N3'] = dict(system='navier_stokes', Q0=ns_smooth((48, )), tf=0.01, L=[1.],
+                               order=3, bts=['periodic'], second_order=True)
+    c['ns2d_smooth_N2'] = dict(system='navier_stokes', Q0=ns_smooth((16, 12)), tf=0.02,
+                               L=[1., 1.], order=2, bts=['periodic', 'transitive'],
+                               second_order=True)
+    # 3-D: BASELINE config 5 at reduced size (oracle = reference + the zero_index fix)
+    c['euler3d_smooth_N2'] = dict(system='euler', Q0=euler_smooth((10, 8, 6)), tf=0.02,
+                                  L=[1., 1., 1.], order=2,
+                                  bts=['periodic', 'periodic', 'transitive'])
+    c['ns3d_taylor_green_N3'] = dict(system='navier_stokes', Q0=taylor_green((6, 6, 6)),
+                                     tf=0.05, L=[2 * np.pi] * 3, order=3,
+                                     bts=['periodic'] * 3, second_order=True)
     return c

@@ -31,16 +31,28 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'weno.npz'), **out)
 
     sol = {}
+    rng = np.random.default_rng(2024)
     for name, c in cases.solver_cases().items():
         ndim = c['Q0'].ndim - 1
         lib = 'libpypde_ref3d.so' if ndim == 3 else 'libpypde_ref.so'
         F, B, S = R.system_callbacks(c['system'], ndim)
-        ret = R.pde_solver(c['Q0'], c['tf'], c['L'], F=F, B=B, S=S, boundaryTypes=c['bts'],
-                           order=c['order'], ndt=1, flux=c.get('flux', 'rusanov'),
-                           stiff=c.get('stiff', False), nThreads=1,
-                           secondOrder=c.get('second_order', False), lib=lib)
-        sol[name] = ret[0]
-        print(name, ret[0].shape, float(np.abs(ret[0]).max()))
+
+        def run(Q0):
+            return R.pde_solver(Q0, c['tf'], c['L'], F=F, B=B, S=S, boundaryTypes=c['bts'],
+                                order=c['order'], ndt=1, flux=c.get('flux', 'rusanov'),
+                                stiff=c.get('stiff', False), nThreads=4,
+                                secondOrder=c.get('second_order', False), lib=lib)[0]
+
+        sol[name] = run(c['Q0'])
+        # the reference's own round-off self-noise: the same run with every entry of
+        # the initial data moved by +-1 ulp.  Parity tolerances are
+        # max(stated tolerance, 4 x this).
+        Qp = np.where(rng.random(c['Q0'].shape) < 0.5, np.nextafter(c['Q0'], np.inf),
+                      np.nextafter(c['Q0'], -np.inf))
+        noise = float(np.abs(run(Qp) - sol[name]).max() / np.abs(sol[name]).max())
+        sol[name + '__noise'] = np.array(noise)
+        print('%-26s %-14s max|u| %.6f  self-noise %.2e' % (name, sol[name].shape[:-1],
+                                                           float(np.abs(sol[name]).max()), noise))
     np.savez_compressed(os.path.join(HERE, 'solver.npz'), **sol)
 
     # tables of the reference (poly/basis.cpp etc.) for N = 2, 3, 4

@@ -9,15 +9,16 @@ Tolerances (relative L-infinity, max|a-b|/max|b|):
   * dt: 1e-7 — the reference's wave speeds are spectral radii of forward-
     difference Jacobians (h ~ 1.5e-8), which turn 1-ulp input differences into
     ~1e-8 relative differences (SURVEY 7.3-H1b);
-  * solutions after a fixed number of steps: 1e-10 on smooth data — the
-    tolerance BASELINE.json states for non-stiff systems; 1e-7 on shock data,
-    where the reference's own 1-ulp self-noise reaches 1.6e-7.
+  * solutions after a fixed number of steps: max(1e-10, 10 x the reference's own
+    +-1 ulp self-noise on that case) — 1e-10 is the tolerance BASELINE.json states
+    for non-stiff systems; the self-noise (stored with the golden fixtures) exceeds
+    it on shock data and with viscous fluxes (conftest.parity_tolerance).
 """
 import numpy as np
 import pytest
 
 import cases
-from conftest import rel_linf
+from conftest import parity_tolerance, rel_linf
 from oracle import ader_weno as O
 from oracle import systems as SY
 import pypde_b200
@@ -74,22 +75,13 @@ def run_gpu(c, ndt=1, **kw):
     return out, Q0
 
 
-SMOOTH = ['euler1d_smooth_N3', 'euler2d_smooth_N3', 'euler2d_smooth_N2', 'advect_nc_1d_N3',
-          'advect_nc_2d_N2']
-SHOCK = ['sod_short_N3', 'euler2d_explosion_N3', 'sod_N2']
-
-
-@pytest.mark.parametrize('name', SMOOTH)
-def test_solver_golden_smooth(golden, name):
+@pytest.mark.parametrize('name', list(cases.solver_cases()))
+def test_solver_golden(golden, name):
+    """Every golden case (1-D/2-D/3-D, Euler / non-conservative+source / viscous,
+    smooth and shock data, BASELINE config 1 in full) through pde_solver."""
     out, Q0 = run_gpu(cases.solver_cases()[name])
-    assert rel_linf(out[0], golden['solver'][name]) < 1e-10
+    assert rel_linf(out[0], golden['solver'][name]) < parity_tolerance(golden['solver'], name)
     assert np.array_equal(Q0, out[-1])       # in-place update of Q0, as the reference
-
-
-@pytest.mark.parametrize('name', SHOCK)
-def test_solver_golden_shock(golden, name):
-    out, _ = run_gpu(cases.solver_cases()[name])
-    assert rel_linf(out[0], golden['solver'][name]) < 1e-7
 
 
 def test_ret_row_semantics():
@@ -110,12 +102,16 @@ def test_ret_row_semantics():
     ('euler', (20, 16), 3, ['periodic', 'transitive']), ('euler', (20, 16), 2, ['periodic', 'periodic']),
     ('advect_nc', (32, ), 3, ['periodic']), ('advect_nc', (14, 10), 2, ['transitive', 'periodic']),
     ('euler', (10, 8, 6), 2, ['periodic', 'periodic', 'transitive']),
-    ('advect_nc', (6, 8, 7), 3, ['periodic', 'periodic', 'periodic'])])
+    ('advect_nc', (6, 8, 7), 3, ['periodic', 'periodic', 'periodic']),
+    ('navier_stokes', (40, ), 3, ['periodic']),
+    ('navier_stokes', (14, 12), 2, ['transitive', 'periodic']),
+    ('navier_stokes', (6, 5, 7), 2, ['periodic', 'periodic', 'periodic'])])
 def test_stages_vs_oracle(system, shape, N, bts):
     ndim = len(shape)
     s = SY.SYSTEMS[system](ndim)
     F, B, S, V = cuda_sources(system, ndim)
-    u = cases.euler_smooth(shape) if system == 'euler' else cases.advect_nc_smooth(shape)
+    u = {'euler': cases.euler_smooth, 'advect_nc': cases.advect_nc_smooth,
+         'navier_stokes': cases.ns_smooth}[system](shape)
     L = [1.] * ndim
     dX = np.array([1. / n for n in shape])
     bt = [BT[b] for b in bts]
@@ -126,12 +122,15 @@ def test_stages_vs_oracle(system, shape, N, bts):
     for k in range(3):
         tg, dtg, nan = sol.step()
         stg = {}
-        un, dt = O.step(u, t, k, 10., dX, bt, s['F'], s['B'], s['S'], N, 0.9, stages=stg)
+        un, dt = O.step(u, t, k, 10., dX, bt, s['F'], s['B'], s['S'], N, 0.9,
+                        second_order=s['second_order'], stages=stg)
         assert not nan
         assert np.array_equal(sol.read_stage('ub').reshape(stg['ub'].shape), stg['ub'])
         assert rel_linf(sol.read_stage('w').reshape(stg['w'].shape), stg['w']) < (1e-11 if ndim < 3 else 1e-10)
-        assert abs(dtg - dt) / dt < 1e-7
-        assert rel_linf(sol.get_state(), un) < 1e-10
+        # viscous bounds difference F w.r.t. grad q, where h ~ 1.5e-8 is large
+        # against the entries: their noise is ~1e-6 relative
+        assert abs(dtg - dt) / dt < (1e-7 if not s['second_order'] else 1e-5)
+        assert rel_linf(sol.get_state(), un) < (1e-10 if not s['second_order'] else 1e-8)
         u, t = un, t + dt
         sol.set_state(u)
     sol.close()

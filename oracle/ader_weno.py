@@ -449,13 +449,16 @@ def fv_apply(u, qh, dt, F, B, S, dX, N, flux=RUSANOV, second_order=False, exact_
 # solvers/iterator.cpp:38-151
 # ---------------------------------------------------------------------------
 def step(u, t, count, tf, dX, boundary_types, F, B, S, N, cfl, flux=RUSANOV,
-         second_order=False, exact_b=False, stages=None):
+         second_order=False, exact_b=False, stages=None, stiff=False):
     """One time step; returns (u_new, dt)."""
     ndim = len(dX)
     ub = boundaries(u, boundary_types, N)
     w = weno(ub, N, ndim)
     dt = time_step(w, F, B, dX, N, cfl, tf, second_order, t, count)
-    qh = predictor(w, dt, F, B, S, dX, N, exact_b)
+    if stiff:
+        qh = predictor_stiff(w, dt, F, B, S, dX, N, exact_b)
+    else:
+        qh = predictor(w, dt, F, B, S, dX, N, exact_b)
     qh = qh.reshape(w.shape[:ndim] + qh.shape[1:])
     un = fv_apply(u, qh, dt, F, B, S, dX, N, flux, second_order, exact_b)
     if stages is not None:
@@ -464,8 +467,9 @@ def step(u, t, count, tf, dX, boundary_types, F, B, S, N, cfl, flux=RUSANOV,
 
 
 def pde_solver(Q0, tf, L, F=None, B=None, S=None, boundary_types=None, cfl=0.9, order=2,
-               ndt=100, flux=RUSANOV, second_order=False, max_steps=None, exact_b=False):
-    """Restates iterator.cpp:99-150 (non-stiff predictor).  Returns (ret, nsteps)."""
+               ndt=100, flux=RUSANOV, second_order=False, max_steps=None, exact_b=False,
+               stiff=False):
+    """Restates iterator.cpp:99-150.  Returns (ret, nsteps)."""
     u = np.array(Q0, dtype=float)
     ndim = u.ndim - 1
     nX = u.shape[:-1]
@@ -476,7 +480,7 @@ def pde_solver(Q0, tf, L, F=None, B=None, S=None, boundary_types=None, cfl=0.9, 
     t, count, push = 0., 0, 0
     while t < tf:
         u, dt = step(u, t, count, tf, dX, boundary_types, F, B, S, order, cfl, flux,
-                     second_order, exact_b)
+                     second_order, exact_b, stiff=stiff)
         t += dt
         count += 1
         if t >= (push + 1) / ndt * tf and push < ndt:
@@ -488,3 +492,198 @@ def pde_solver(Q0, tf, L, F=None, B=None, S=None, boundary_types=None, cfl=0.9, 
             break
     ret[ndt - 1] = u
     return ret, count
+
+
+# ---------------------------------------------------------------------------
+# Stiff predictor: scipy/algos/newton_krylov.cpp:9-183, scipy/algos/lgmres.cpp:6-104,
+# solvers/dg/dg.cpp:128-185.  Per cell, plain loops (small cases only).
+# ---------------------------------------------------------------------------
+MEPS = 2.2204460492503131e-16   # types.h:18
+
+
+def lgmres(matvec, b, outer_v, tol, maxiter=1, inner_m=30, outer_k=10):
+    """lgmres.cpp:6-104 with psolve = identity, x0 = 0.  outer_v is updated in
+    place (the recycled augmentation vectors persist across Newton iterations)."""
+    n = b.size
+    x = np.zeros(n)
+    b_norm = np.linalg.norm(b)
+    if b_norm == 0.:
+        b_norm = 1.
+    for _ in range(maxiter):
+        r_outer = matvec(x) - b
+        r_norm = np.linalg.norm(r_outer)
+        if r_norm <= tol * b_norm or r_norm <= tol:
+            break
+        vs0 = -r_outer
+        inner_res_0 = np.linalg.norm(vs0)
+        vs0 = vs0 / inner_res_0
+        vs = [vs0]
+        ws = []
+        ind = 1 + inner_m + len(outer_v)
+        H = np.zeros((ind + 1, ind))          # Hessenberg-like matrix, column j-1 = hcur
+        Q = None
+        R = None
+        j = 1
+        while j < ind:
+            if j < len(outer_v) + 1:
+                z = outer_v[j - 1]
+            elif j == len(outer_v) + 1:
+                z = vs0
+            else:
+                z = vs[-1]
+            v_new = matvec(z)
+            v_new_norm = np.linalg.norm(v_new)
+            hcur = np.zeros(j + 1)
+            for i, v in enumerate(vs):
+                alpha = np.dot(v, v_new)
+                hcur[i] = alpha
+                v_new = v_new - alpha * v
+            hcur[j] = np.linalg.norm(v_new)
+            v_new = v_new / hcur[j]
+            vs.append(v_new)
+            ws.append(z)
+            H[:j + 1, j - 1] = hcur
+            # lgmres.cpp:70-77 re-factorises [Q R | hcur] by Householder QR; the
+            # least-squares quantities below do not depend on how QR is computed
+            Q, R = np.linalg.qr(H[:j + 1, :j], mode='complete')
+            inner_res = abs(Q[0, j]) * inner_res_0
+            if inner_res <= tol * inner_res_0 or hcur[j] <= MEPS * v_new_norm:
+                break
+            j += 1
+        if j == ind:
+            j -= 1
+        # lgmres.cpp:86-88: y = R(0:j,0:j)^-1 Q(0,0:j)^T * inner_res_0
+        y = np.linalg.solve(R[:j, :j], Q[0, :j]) * inner_res_0
+        dx = y[0] * ws[0]
+        for i in range(1, j):
+            dx = dx + y[i] * ws[i]
+        nx = np.linalg.norm(dx)
+        if nx > 0.:
+            outer_v.append(dx / nx)
+        while len(outer_v) > outer_k:
+            outer_v.pop(0)
+        x = x + dx
+    return x
+
+
+def _armijo(phi, phi0):
+    """newton_krylov.cpp:91-142 (scalar_search_armijo with c1 = 1e-4, amin = 1e-2)."""
+    c1, amin = 1e-4, 1e-2
+    phi_a0 = phi(1.)
+    if phi_a0 <= phi0 - c1 * phi0:
+        return 1.
+    alpha1 = phi0 / (2. * phi_a0)
+    phi_a1 = phi(alpha1)
+    if phi_a1 <= phi0 - c1 * alpha1 * phi0:
+        return alpha1
+    while alpha1 > amin:
+        factor = alpha1 * alpha1 * (alpha1 - 1)
+        a = phi_a1 - phi0 + phi0 * alpha1 - alpha1 * alpha1 * phi_a0
+        a /= factor
+        b = -(phi_a1 - phi0 + phi0 * alpha1) + alpha1 * alpha1 * alpha1 * phi_a0
+        b /= factor
+        alpha2 = (-b + np.sqrt(abs(b * b + 3 * a * phi0))) / (3. * a)
+        phi_a2 = phi(alpha2)
+        if phi_a2 <= phi0 - c1 * alpha2 * phi0:
+            return alpha2
+        if (alpha1 - alpha2) > alpha1 / 2.0 or (1 - alpha2 / alpha1) < 0.96:
+            alpha2 = alpha1 / 2.0
+        alpha1 = alpha2
+        phi_a0 = phi_a1
+        phi_a1 = phi_a2
+    return 1.
+
+
+def nonlin_solve(func, x, f_tol, counters=None):
+    """newton_krylov.cpp:144-183 with the defaults f_rtol = x_tol = x_rtol = DBL_MAX.
+    The outer `dx` is never updated (the inner one shadows it, :153,:167), so the
+    termination test (:61-76) reduces to  ||F||inf <= f_tol AND ||x||inf >= 1,
+    or ||F||inf == 0."""
+    x = x.copy()
+    gamma, eta_max, eta_treshold, eta = 0.9, 0.9999, 0.1, 1e-3
+    Fx = func(x)
+    Fx_norm = np.abs(Fx).max()            # maxnorm
+    rdiff = MEPS**0.5
+    outer_v = []
+    f0_norm = [0.]
+
+    def check(f, xx):
+        f_norm = np.abs(f).max()
+        x_norm = np.abs(xx).max()
+        dx_norm = DBL_MAX
+        if f0_norm[0] == 0.:
+            f0_norm[0] = f_norm
+        if f_norm == 0.:
+            return True
+        return (f_norm <= f_tol and f_norm / DBL_MAX <= f0_norm[0]) and \
+               (dx_norm <= DBL_MAX and dx_norm / DBL_MAX <= x_norm)
+
+    x0, f0 = x.copy(), Fx.copy()
+    maxiter = 3 * (x.size + 1)
+    nit = 0
+    for _ in range(maxiter):
+        if check(Fx, x):
+            break
+        nit += 1
+        omega = rdiff * max(1., np.abs(x0).max()) / max(1., np.abs(f0).max())
+
+        def matvec(v):
+            nv = np.linalg.norm(v)
+            if nv == 0.:
+                return 0. * v
+            sc = omega / nv
+            return (func(x0 + sc * v) - f0) / sc
+
+        tol = min(eta, eta * Fx_norm)
+        dx = -lgmres(matvec, Fx, outer_v, tol)
+        # _nonlin_line_search, newton_krylov.cpp:125-142
+        cache = {'s': 0., 'phi': float(np.dot(Fx, Fx)), 'F': Fx}
+
+        def phi(s):
+            if s == cache['s']:
+                return cache['phi']
+            v = func(x + s * dx)
+            cache.update(s=s, phi=float(np.dot(v, v)), F=v)
+            return cache['phi']
+
+        s = _armijo(phi, cache['phi'])
+        x = x + s * dx
+        Fx = cache['F'] if s == cache['s'] else func(x)
+        Fx_norm_new = np.linalg.norm(Fx)       # note: 2-norm here (:170), max-norm at :155
+        x0, f0 = x.copy(), Fx.copy()
+        eta_A = gamma * Fx_norm_new * Fx_norm_new / (Fx_norm * Fx_norm)
+        if gamma * eta * eta < eta_treshold:
+            eta = min(eta_max, eta_A)
+        else:
+            eta = min(eta_max, max(eta_A, gamma * eta * eta))
+        Fx_norm = Fx_norm_new
+    if counters is not None:
+        counters.append(nit)
+    return x
+
+
+def predictor_stiff(w, dt, F, B, S, dX, N, exact_b=False, counters=None):
+    """dg.cpp:128-185,204-224 with STIFF = true: per cell Newton-Krylov on
+    obj(q) = rhs(q) - (DG_MAT (x) W) q."""
+    T = tables(N)
+    ndim = len(dX)
+    wc = w.reshape((-1, ) + w.shape[-1 - ndim:])
+    ncell = wc.shape[0]
+    wp = weight_products(ndim, T)
+    out = np.empty((ncell, N) + wc.shape[1:])
+    for cidx in range(ncell):
+        wi = wc[cidx:cidx + 1]
+        Ww = dg_initial_condition(wi, N, ndim)
+        q0 = np.repeat(wi[:, None], N, axis=1)
+        shape = q0.shape
+
+        def obj(qv):
+            q = qv.reshape(shape)
+            tmp = dg_rhs(q, Ww, dt, F, B, S, dX, N, exact_b)
+            # dg.cpp:135-151: tmp(t) -= DG_MAT(t,k) * prod(w) * q(k)
+            tmp = tmp - np.einsum('tk,nk...->nt...', T.dgmat, q) * wp[..., None]
+            return tmp.ravel()
+
+        res = nonlin_solve(obj, q0.ravel(), DG_TOL, counters)
+        out[cidx] = res.reshape(shape)[0]
+    return out

@@ -190,6 +190,12 @@ void choose_block_shapes(KernelConfig &c) {
   while (fpb > 1 && (size_t)fpb * NP * sm_pt > 48 * 1024)
     fpb--;
   c.faces_fpb = fpb;
+  // k_dg_stiff: one warp per cell, (3+ndim) n doubles of shared memory per warp
+  const size_t sm_warp = (size_t)(3 + c.ndim) * NT * c.V * 8;
+  int wpb = 4;
+  while (wpb > 1 && wpb * sm_warp > 96 * 1024)
+    wpb--;
+  c.stiff_wpb = wpb;
 }
 
 std::vector<std::string> specialisation_defines(const KernelConfig &c) {
@@ -210,7 +216,8 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_EXACT_B_PRODUCT", exact_b_product() ? 1 : 0),
           kv("PDE_EIG_QR_ONLY", getenv("PYPDE_B200_EIG_QR_ONLY") ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
-          kv("PDE_FACES_FPB", c.faces_fpb)};
+          kv("PDE_FACES_FPB", c.faces_fpb),
+          kv("PDE_STIFF_WPB", c.stiff_wpb)};
   // tuning experiments: PYPDE_B200_EXTRA_DEFINES="PDE_X=1;PDE_Y=0"
   if (const char *e = getenv("PYPDE_B200_EXTRA_DEFINES")) {
     std::string all(e);

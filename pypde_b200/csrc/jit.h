@@ -16,6 +16,7 @@ struct KernelConfig {
   bool stiff = false, useF = false, useB = false, useS = false, secondOrder = false;
   int dg_cpb = 1;    // cells per block in k_dg
   int faces_fpb = 1; // faces per block in k_faces
+  int stiff_wpb = 4; // warps (cells) per block in k_dg_stiff
 };
 
 // Chooses the block shapes for a configuration (threads <= 256 where possible,

@@ -91,6 +91,8 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   get(k_fp64_peak, "k_fp64_peak");
   if (cfg.useF)
     get(k_wavespeeds, "k_wavespeeds");
+  if (cfg.stiff)
+    get(k_dg_stiff, "k_dg_stiff");
 }
 
 Module::~Module() {
@@ -109,9 +111,6 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     throw std::runtime_error("pypde_b200: V must be >= 1");
   if (cfg_.N < 1)
     throw std::runtime_error("pypde_b200: order N must be >= 1");
-  if (cfg_.stiff)
-    throw std::runtime_error("pypde_b200: the stiff (Newton-Krylov) predictor is not built yet; "
-                             "pass stiff=False");
   if (cfg_.flux != 0 && cfg_.useF)
     throw std::runtime_error("pypde_b200: only flux='rusanov' is built yet");
   choose_block_shapes(cfg_);
@@ -204,6 +203,23 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   check(d.StreamCreate(&stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
   own_stream_ = true;
 
+  if (cfg_.stiff) {
+    // one warp per cell; global workspace per warp (kernels.cuh: NK_WORK)
+    const size_t n = (size_t)N * Nd * V;
+    const size_t nk_work = 5 * n + 41 * n + 10 * n + 42 * 41 + 6 * 41;
+    stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
+    const size_t smem_warp = (3 + nd) * n * D;
+    if (smem_warp > 220 * 1024)
+      throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
+    long blocks = (ncellw_ + stiff_wpb_ - 1) / stiff_wpb_;
+    long cap = (long)sms_ * 4;
+    stiff_blocks_ = blocks < cap ? blocks : cap;
+    stiff_work_.alloc((size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D);
+    if (stiff_wpb_ * smem_warp > 48 * 1024)
+      check(d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                               (int)(stiff_wpb_ * smem_warp)),
+            "cuFuncSetAttribute(k_dg_stiff smem)");
+  }
   // dynamic shared memory opt-in
   const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;
   if (dg_smem > 48 * 1024)
@@ -481,7 +497,11 @@ void Solver::step_async() {
     void *args[] = {&state_.p};
     launch(mod_->k_dt, 1, 1, 0, args, "k_dt");
   }
-  {
+  if (cfg_.stiff) {
+    const size_t smem = (size_t)stiff_wpb_ * (3 + nd) * N * Nd * V * sizeof(double);
+    void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p, &stiff_work_.p};
+    launch(mod_->k_dg_stiff, (unsigned)stiff_blocks_, 32 * stiff_wpb_, smem, args, "k_dg_stiff");
+  } else {
     const unsigned block = cfg_.dg_cpb * N * Nd;
     const size_t smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * sizeof(double);
     long nblocks = (ncellw_ + cfg_.dg_cpb - 1) / cfg_.dg_cpb;

@@ -59,7 +59,7 @@ public:
   CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
-             k_wavespeeds = nullptr;
+             k_wavespeeds = nullptr, k_dg_stiff = nullptr;
 };
 
 class Solver {
@@ -121,6 +121,9 @@ private:
   CUstream stream_ = nullptr;
   bool own_stream_ = false;
 
+  DeviceBuffer stiff_work_;
+  int stiff_wpb_ = 4;
+  long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,
       flx_[3], state_;
   CUdeviceptr u_ = 0;

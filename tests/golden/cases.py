@@ -83,6 +83,31 @@ def ns_smooth(shape):
     return Q
 
 
+def reactive_state(rho, p, vel, lam):
+    """Q = [rho, rho E, rho v.., rho lambda], E = p/((g-1) rho) + v^2/2 + Qc (lambda - 1)."""
+    rho = np.asarray(rho, dtype=float)
+    nd = len(vel)
+    Q = np.zeros(rho.shape + (3 + nd, ))
+    Q[..., 0] = rho
+    Q[..., 1] = p / (G - 1) + rho * sum(np.asarray(v) * v for v in vel) / 2 + rho * (lam - 1.)
+    for i, v in enumerate(vel):
+        Q[..., 2 + i] = rho * v
+    Q[..., 2 + nd] = rho * lam
+    return Q
+
+
+def reactive_disc(shape, smooth=False):
+    """BASELINE config 3 IC: burnt disc (rho, p, lambda) = (2.8, 2.0, 0) in
+    unburnt gas (2.0, 0.8, 1); every state has max|Q| well above 1, as the reference's
+    Newton termination rule needs.  smooth=True blends the two states with a tanh."""
+    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape)))
+    s = 0.5 * (1 - np.tanh((r - 0.25) / 0.08)) if smooth else (r < 0.25).astype(float)
+    rho = 2.0 + 0.8 * s
+    p = 0.8 + 1.2 * s
+    lam = 1.0 - s
+    return reactive_state(rho, p, [np.zeros(shape)] * len(shape), lam)
+
+
 def weno_kat_input():
     return np.array([1, 2, 4, 7, 11, 16, 22.]).reshape(7, 1)
 
@@ -123,4 +148,16 @@ def solver_cases():
     c['ns3d_taylor_green_N3'] = dict(system='navier_stokes', Q0=taylor_green((6, 6, 6)),
                                      tf=0.05, L=[2 * np.pi] * 3, order=3,
                                      bts=['periodic'] * 3, second_order=True)
+    # stiff = True: Newton-Krylov predictor (dg.cpp:173-185)
+    c['euler1d_smooth_N3_stiff'] = dict(system='euler', Q0=euler_smooth((32, )), tf=0.02,
+                                        L=[1.], order=3, bts=['periodic'], stiff=True)
+    c['advect_nc_2d_N2_stiff'] = dict(system='advect_nc', Q0=advect_nc_smooth((10, 8)),
+                                      tf=0.06, L=[1., 1.], order=2,
+                                      bts=['periodic', 'periodic'], stiff=True)
+    c['reactive1d_smooth_N3_stiff'] = dict(system='reactive_euler',
+                                           Q0=reactive_disc((40, ), smooth=True), tf=0.03,
+                                           L=[1.], order=3, bts=['transitive'], stiff=True)
+    c['reactive2d_disc_N3_stiff'] = dict(system='reactive_euler', Q0=reactive_disc((12, 12)),
+                                         tf=0.02, L=[1., 1.], order=3,
+                                         bts=['transitive', 'transitive'], stiff=True)
     return c

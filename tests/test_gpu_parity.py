@@ -79,8 +79,12 @@ def run_gpu(c, ndt=1, **kw):
 def test_solver_golden(golden, name):
     """Every golden case (1-D/2-D/3-D, Euler / non-conservative+source / viscous,
     smooth and shock data, BASELINE config 1 in full) through pde_solver."""
-    out, Q0 = run_gpu(cases.solver_cases()[name])
-    assert rel_linf(out[0], golden['solver'][name]) < parity_tolerance(golden['solver'], name)
+    c = cases.solver_cases()[name]
+    out, Q0 = run_gpu(c)
+    # BASELINE.json: 1e-10 for non-stiff systems, 1e-8 where the stiff Newton solve is active
+    stated = 1e-8 if c.get('stiff') else 1e-10
+    assert rel_linf(out[0], golden['solver'][name]) < parity_tolerance(golden['solver'], name,
+                                                                       stated)
     assert np.array_equal(Q0, out[-1])       # in-place update of Q0, as the reference
 
 

@@ -97,6 +97,9 @@ int pypde_b200_tables(int N, double *nodes, double *wghts, double *derv, double 
 int pypde_b200_host_spectral_radius(const double *A, int n, int qr_only, double *rho,
                                     int *path);
 
+/* Same, for the Osher/Roe dissipation y = |A| x = Re(R |Lambda| R^-1 x). */
+int pypde_b200_host_abs_matrix_apply(const double *A, int n, const double *x, double *y);
+
 /* JIT only (no GPU needed): specialise + link the kernels for a configuration
  * and return the sm_100a cubin size (and optionally the cubin).  Used by the
  * CPU test-suite and by build(). */

@@ -646,4 +646,461 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
   return spectral_radius_qr<n>(a);
 }
 
+// ---------------------------------------------------------------------------
+// D2: y = |A| x for a general real n x n matrix, |A| = R |Lambda| R^-1 — the
+// dissipation matrix of the Osher and Roe fluxes (reference fluxes.cpp:36-41,
+// 64-69: Eigen EigenSolver + complex column-pivoted QR solve, real part taken).
+// Real arithmetic throughout: elimination to Hessenberg form with accumulated
+// transformations, Francis double-shift QR to real Schur form with accumulation,
+// back-substitution for the eigenvectors (the classical EISPACK elmhes / eltran /
+// hqr2 sequence), giving A W = W D with W real: column j for a real eigenvalue,
+// columns (j, j+1) = (Re v, Im v) for a complex pair, whose 2 x 2 block of D has
+// modulus |lambda| times a rotation — so |A| = W diag(|lambda_j|) W^-1 with the
+// same modulus on both columns of a pair, and y = W (|lambda| o (W^-1 x)) by one
+// real LU solve with partial pivoting.  a is destroyed.  Returns false if the QR
+// iteration did not converge (y is then left untouched).
+// ---------------------------------------------------------------------------
+template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *x, double *y) {
+#define A_(i, j) a[(i) * n + (j)]
+#define Z_(i, j) zz[(i) * n + (j)]
+  double zz[n * n], wr[n], wi[n];
+  int perm[n];
+  if (n == 1) {
+    y[0] = fabs(a[0]) * x[0];
+    return true;
+  }
+  // --- elmhes with the permutation recorded
+  for (int m = 1; m < n - 1; m++) {
+    double xx = 0.;
+    int i = m;
+    for (int j = m; j < n; j++)
+      if (fabs(A_(j, m - 1)) > fabs(xx)) {
+        xx = A_(j, m - 1);
+        i = j;
+      }
+    perm[m] = i;
+    if (i != m) {
+      for (int j = m - 1; j < n; j++) {
+        double tmp = A_(i, j);
+        A_(i, j) = A_(m, j);
+        A_(m, j) = tmp;
+      }
+      for (int j = 0; j < n; j++) {
+        double tmp = A_(j, i);
+        A_(j, i) = A_(j, m);
+        A_(j, m) = tmp;
+      }
+    }
+    if (xx != 0.) {
+      for (i = m + 1; i < n; i++) {
+        double yy = A_(i, m - 1);
+        if (yy != 0.) {
+          yy /= xx;
+          A_(i, m - 1) = yy;
+          for (int j = m; j < n; j++)
+            A_(i, j) -= yy * A_(m, j);
+          for (int j = 0; j < n; j++)
+            A_(j, m) += yy * A_(j, i);
+        }
+      }
+    }
+  }
+  // --- eltran: accumulate the similarity transformations
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      Z_(i, j) = i == j ? 1. : 0.;
+  for (int mp = n - 2; mp > 0; mp--) {
+    for (int k = mp + 1; k < n; k++)
+      Z_(k, mp) = A_(k, mp - 1);
+    const int i = perm[mp];
+    if (i != mp) {
+      for (int j = mp; j < n; j++) {
+        Z_(mp, j) = Z_(i, j);
+        Z_(i, j) = 0.;
+      }
+      Z_(i, mp) = 1.;
+    }
+  }
+  for (int i = 2; i < n; i++)
+    for (int j = 0; j < i - 1; j++)
+      A_(i, j) = 0.;
+
+  // --- hqr2: real Schur form with accumulation
+  double anorm = 0.;
+  for (int i = 0; i < n; i++)
+    for (int j = (i > 0 ? i - 1 : 0); j < n; j++)
+      anorm += fabs(A_(i, j));
+  int nn = n - 1;
+  double t = 0., p = 0., q = 0., r = 0., s = 0., w, xx, yy, z;
+  while (nn >= 0) {
+    int its = 0, l;
+    do {
+      for (l = nn; l > 0; l--) {
+        s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
+        if (s == 0.)
+          s = anorm;
+        if (fabs(A_(l, l - 1)) <= DBL_EPS * s) {
+          A_(l, l - 1) = 0.;
+          break;
+        }
+      }
+      xx = A_(nn, nn);
+      if (l == nn) { // one root
+        wr[nn] = A_(nn, nn) = xx + t;
+        wi[nn] = 0.;
+        nn--;
+      } else {
+        yy = A_(nn - 1, nn - 1);
+        w = A_(nn, nn - 1) * A_(nn - 1, nn);
+        if (l == nn - 1) { // two roots
+          p = 0.5 * (yy - xx);
+          q = p * p + w;
+          z = sqrt(fabs(q));
+          xx += t;
+          A_(nn, nn) = xx;
+          A_(nn - 1, nn - 1) = yy + t;
+          if (q >= 0.) { // real pair
+            z = p + (p >= 0. ? fabs(z) : -fabs(z));
+            wr[nn - 1] = wr[nn] = xx + z;
+            if (z != 0.)
+              wr[nn] = xx - w / z;
+            wi[nn - 1] = wi[nn] = 0.;
+            xx = A_(nn, nn - 1);
+            s = fabs(xx) + fabs(z);
+            p = xx / s;
+            q = z / s;
+            r = sqrt(p * p + q * q);
+            p /= r;
+            q /= r;
+            for (int j = nn - 1; j < n; j++) { // row modification
+              z = A_(nn - 1, j);
+              A_(nn - 1, j) = q * z + p * A_(nn, j);
+              A_(nn, j) = q * A_(nn, j) - p * z;
+            }
+            for (int i = 0; i <= nn; i++) { // column modification
+              z = A_(i, nn - 1);
+              A_(i, nn - 1) = q * z + p * A_(i, nn);
+              A_(i, nn) = q * A_(i, nn) - p * z;
+            }
+            for (int i = 0; i < n; i++) { // accumulate
+              z = Z_(i, nn - 1);
+              Z_(i, nn - 1) = q * z + p * Z_(i, nn);
+              Z_(i, nn) = q * Z_(i, nn) - p * z;
+            }
+          } else { // complex pair
+            wr[nn - 1] = wr[nn] = xx + p;
+            wi[nn - 1] = z;
+            wi[nn] = -z;
+          }
+          nn -= 2;
+        } else { // no root yet: QR step
+          if (its >= 60)
+            return false;
+          if (its == 10 || its == 20) { // exceptional shift
+            t += xx;
+            for (int i = 0; i <= nn; i++)
+              A_(i, i) -= xx;
+            s = fabs(A_(nn, nn - 1)) + fabs(A_(nn - 1, nn - 2));
+            yy = xx = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          int m;
+          for (m = nn - 2; m >= l; m--) {
+            z = A_(m, m);
+            r = xx - z;
+            s = yy - z;
+            p = (r * s - w) / A_(m + 1, m) + A_(m, m + 1);
+            q = A_(m + 1, m + 1) - z - r - s;
+            r = A_(m + 2, m + 1);
+            s = fabs(p) + fabs(q) + fabs(r);
+            p /= s;
+            q /= s;
+            r /= s;
+            if (m == l)
+              break;
+            double u = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
+            double v = fabs(p) * (fabs(A_(m - 1, m - 1)) + fabs(z) + fabs(A_(m + 1, m + 1)));
+            if (u <= DBL_EPS * v)
+              break;
+          }
+          for (int i = m; i < nn - 1; i++) {
+            A_(i + 2, i) = 0.;
+            if (i != m)
+              A_(i + 2, i - 1) = 0.;
+          }
+          for (int k = m; k < nn; k++) {
+            if (k != m) {
+              p = A_(k, k - 1);
+              q = A_(k + 1, k - 1);
+              r = 0.;
+              if (k + 1 != nn)
+                r = A_(k + 2, k - 1);
+              if ((xx = fabs(p) + fabs(q) + fabs(r)) != 0.) {
+                p /= xx;
+                q /= xx;
+                r /= xx;
+              }
+            }
+            double sq = sqrt(p * p + q * q + r * r);
+            s = p >= 0. ? sq : -sq;
+            if (s != 0.) {
+              if (k == m) {
+                if (l != m)
+                  A_(k, k - 1) = -A_(k, k - 1);
+              } else
+                A_(k, k - 1) = -s * xx;
+              p += s;
+              xx = p / s;
+              yy = q / s;
+              z = r / s;
+              q /= p;
+              r /= p;
+              for (int j = k; j < n; j++) { // row modification
+                p = A_(k, j) + q * A_(k + 1, j);
+                if (k + 1 != nn) {
+                  p += r * A_(k + 2, j);
+                  A_(k + 2, j) -= p * z;
+                }
+                A_(k + 1, j) -= p * yy;
+                A_(k, j) -= p * xx;
+              }
+              int mmin = nn < k + 3 ? nn : k + 3;
+              for (int i = 0; i <= mmin; i++) { // column modification
+                p = xx * A_(i, k) + yy * A_(i, k + 1);
+                if (k + 1 != nn) {
+                  p += z * A_(i, k + 2);
+                  A_(i, k + 2) -= p * r;
+                }
+                A_(i, k + 1) -= p * q;
+                A_(i, k) -= p;
+              }
+              for (int i = 0; i < n; i++) { // accumulate
+                p = xx * Z_(i, k) + yy * Z_(i, k + 1);
+                if (k + 1 != nn) {
+                  p += z * Z_(i, k + 2);
+                  Z_(i, k + 2) -= p * r;
+                }
+                Z_(i, k + 1) -= p * q;
+                Z_(i, k) -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l + 1 < nn);
+  }
+
+  // --- back-substitution: eigenvectors of the quasi-triangular matrix
+  if (anorm != 0.) {
+    for (nn = n - 1; nn >= 0; nn--) {
+      p = wr[nn];
+      q = wi[nn];
+      const int na = nn - 1;
+      if (q == 0.) { // real vector
+        int m = nn;
+        A_(nn, nn) = 1.;
+        for (int i = nn - 1; i >= 0; i--) {
+          w = A_(i, i) - p;
+          r = 0.;
+          for (int j = m; j <= nn; j++)
+            r += A_(i, j) * A_(j, nn);
+          if (wi[i] < 0.) {
+            z = w;
+            s = r;
+          } else {
+            m = i;
+            if (wi[i] == 0.) {
+              t = w;
+              if (t == 0.)
+                t = DBL_EPS * anorm;
+              A_(i, nn) = -r / t;
+            } else { // solve the 2 x 2 block
+              xx = A_(i, i + 1);
+              yy = A_(i + 1, i);
+              q = (wr[i] - p) * (wr[i] - p) + wi[i] * wi[i];
+              t = (xx * s - z * r) / q;
+              A_(i, nn) = t;
+              if (fabs(xx) > fabs(z))
+                A_(i + 1, nn) = (-r - w * t) / xx;
+              else
+                A_(i + 1, nn) = (-s - yy * t) / z;
+            }
+            t = fabs(A_(i, nn)); // overflow control
+            if (DBL_EPS * t * t > 1.)
+              for (int j = i; j <= nn; j++)
+                A_(j, nn) /= t;
+          }
+        }
+      } else if (q < 0.) { // complex vector, last component chosen imaginary
+        int m = na;
+        if (fabs(A_(nn, na)) > fabs(A_(na, nn))) {
+          A_(na, na) = q / A_(nn, na);
+          A_(na, nn) = -(A_(nn, nn) - p) / A_(nn, na);
+        } else { // (0, -a[na][nn]) / (a[na][na]-p, q)
+          const double cr = A_(na, na) - p, ci = q, nr = 0., ni = -A_(na, nn);
+          const double den = cr * cr + ci * ci;
+          A_(na, na) = (nr * cr + ni * ci) / den;
+          A_(na, nn) = (ni * cr - nr * ci) / den;
+        }
+        A_(nn, na) = 0.;
+        A_(nn, nn) = 1.;
+        for (int i = nn - 2; i >= 0; i--) {
+          w = A_(i, i) - p;
+          double ra = 0., sa = 0.;
+          for (int j = m; j <= nn; j++) {
+            ra += A_(i, j) * A_(j, na);
+            sa += A_(i, j) * A_(j, nn);
+          }
+          if (wi[i] < 0.) {
+            z = w;
+            r = ra;
+            s = sa;
+          } else {
+            m = i;
+            if (wi[i] == 0.) { // (-ra, -sa) / (w, q)
+              const double den = w * w + q * q;
+              A_(i, na) = (-ra * w - sa * q) / den;
+              A_(i, nn) = (-sa * w + ra * q) / den;
+            } else { // solve the complex 2 x 2 block
+              xx = A_(i, i + 1);
+              yy = A_(i + 1, i);
+              double vr = (wr[i] - p) * (wr[i] - p) + wi[i] * wi[i] - q * q;
+              const double vi = 2. * q * (wr[i] - p);
+              if (vr == 0. && vi == 0.)
+                vr = DBL_EPS * anorm * (fabs(w) + fabs(q) + fabs(xx) + fabs(yy) + fabs(z));
+              { // (x r - z ra + q sa, x s - z sa - q ra) / (vr, vi)
+                const double nr = xx * r - z * ra + q * sa, ni = xx * s - z * sa - q * ra;
+                const double den = vr * vr + vi * vi;
+                A_(i, na) = (nr * vr + ni * vi) / den;
+                A_(i, nn) = (ni * vr - nr * vi) / den;
+              }
+              if (fabs(xx) > fabs(z) + fabs(q)) {
+                A_(i + 1, na) = (-ra - w * A_(i, na) + q * A_(i, nn)) / xx;
+                A_(i + 1, nn) = (-sa - w * A_(i, nn) - q * A_(i, na)) / xx;
+              } else { // (-r - y a[i][na], -s - y a[i][nn]) / (z, q)
+                const double nr = -r - yy * A_(i, na), ni = -s - yy * A_(i, nn);
+                const double den = z * z + q * q;
+                A_(i + 1, na) = (nr * z + ni * q) / den;
+                A_(i + 1, nn) = (ni * z - nr * q) / den;
+              }
+            }
+          }
+          t = fmax(fabs(A_(i, na)), fabs(A_(i, nn))); // overflow control
+          if (DBL_EPS * t * t > 1.)
+            for (int j = i; j <= nn; j++) {
+              A_(j, na) /= t;
+              A_(j, nn) /= t;
+            }
+        }
+      }
+    }
+    // multiply by the transformation matrix: vectors of the original matrix
+    for (int j = n - 1; j >= 0; j--)
+      for (int i = 0; i < n; i++) {
+        z = 0.;
+        for (int k = 0; k <= j; k++)
+          z += Z_(i, k) * A_(k, j);
+        Z_(i, j) = z;
+      }
+  }
+  // --- c = W^-1 x by Householder QR with column pivoting on a copy of W (in a),
+  // rank-revealing as the reference's colPivHouseholderQr().solve(): for a repeated
+  // eigenvalue (v = 0 in gas at rest: a triple zero in 3-D) the back-substituted
+  // vectors can be numerically dependent; pivots below n eps |largest pivot| are
+  // dropped and their coefficients set to zero (the basic solution).
+  double c[n], rhs[n], cn2[n];
+  int cp[n];
+  for (int i = 0; i < n * n; i++)
+    a[i] = zz[i];
+  for (int i = 0; i < n; i++) {
+    rhs[i] = x[i];
+    cp[i] = i;
+  }
+  for (int j = 0; j < n; j++) {
+    double sacc = 0.;
+    for (int i = 0; i < n; i++)
+      sacc += A_(i, j) * A_(i, j);
+    cn2[j] = sacc;
+  }
+  int rank = 0;
+  double maxpiv = 0.;
+  for (int k = 0; k < n; k++) {
+    // pivot: remaining column of largest norm (recomputed: n is small)
+    int piv = k;
+    double best2 = -1.;
+    for (int j = k; j < n; j++) {
+      double sacc = 0.;
+      for (int i = k; i < n; i++)
+        sacc += A_(i, j) * A_(i, j);
+      cn2[j] = sacc;
+      if (sacc > best2) {
+        best2 = sacc;
+        piv = j;
+      }
+    }
+    if (piv != k) {
+      for (int i = 0; i < n; i++) {
+        double tmp = A_(i, k);
+        A_(i, k) = A_(i, piv);
+        A_(i, piv) = tmp;
+      }
+      int ti = cp[k];
+      cp[k] = cp[piv];
+      cp[piv] = ti;
+    }
+    const double nrm = sqrt(best2);
+    if (k == 0)
+      maxpiv = nrm;
+    if (!(nrm > n * DBL_EPS * maxpiv))
+      break;
+    rank = k + 1;
+    // Householder vector for column k, rows k..n-1
+    const double alpha = A_(k, k) >= 0. ? -nrm : nrm;
+    const double v0 = A_(k, k) - alpha;
+    double vnorm2 = v0 * v0;
+    for (int i = k + 1; i < n; i++)
+      vnorm2 += A_(i, k) * A_(i, k);
+    if (vnorm2 > 0.) {
+      const double beta = 2. / vnorm2;
+      for (int j = k + 1; j < n; j++) {
+        double sacc = v0 * A_(k, j);
+        for (int i = k + 1; i < n; i++)
+          sacc += A_(i, k) * A_(i, j);
+        sacc *= beta;
+        A_(k, j) -= sacc * v0;
+        for (int i = k + 1; i < n; i++)
+          A_(i, j) -= sacc * A_(i, k);
+      }
+      double sacc = v0 * rhs[k];
+      for (int i = k + 1; i < n; i++)
+        sacc += A_(i, k) * rhs[i];
+      sacc *= beta;
+      rhs[k] -= sacc * v0;
+      for (int i = k + 1; i < n; i++)
+        rhs[i] -= sacc * A_(i, k);
+    }
+    A_(k, k) = alpha;
+  }
+  for (int i = 0; i < n; i++)
+    c[i] = 0.;
+  for (int i = rank - 1; i >= 0; i--) {
+    double sacc = rhs[i];
+    for (int j = i + 1; j < rank; j++)
+      sacc -= A_(i, j) * c[cp[j]];
+    c[cp[i]] = sacc / A_(i, i);
+  }
+  for (int j = 0; j < n; j++)
+    c[j] *= hypot(wr[j], wi[j]);
+  for (int i = 0; i < n; i++) {
+    double sacc = 0.;
+    for (int j = 0; j < n; j++)
+      sacc += Z_(i, j) * c[j];
+    y[i] = sacc;
+  }
+  return true;
+#undef A_
+#undef Z_
+}
+
 #endif // PYPDE_B200_EIG_CUH

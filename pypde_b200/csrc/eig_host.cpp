@@ -39,3 +39,21 @@ extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_on
     *path = qr_only ? 0 : pth;
   return 0;
 }
+
+extern "C" int pypde_b200_host_abs_matrix_apply(const double *A, int n, const double *x,
+                                                double *y) {
+  if (n < 1 || n > 17 || !A || !x || !y)
+    return 1;
+  std::vector<double> a(A, A + (size_t)n * n);
+  bool ok = false;
+#define CASE(N)                                                                                   \
+  case N:                                                                                         \
+    ok = abs_matrix_apply<N>(a.data(), x, y);                                                     \
+    break;
+  switch (n) {
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11)
+    CASE(12) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17)
+  }
+#undef CASE
+  return ok ? 0 : 2;
+}

@@ -111,8 +111,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     throw std::runtime_error("pypde_b200: V must be >= 1");
   if (cfg_.N < 1)
     throw std::runtime_error("pypde_b200: order N must be >= 1");
-  if (cfg_.flux != 0 && cfg_.useF)
-    throw std::runtime_error("pypde_b200: only flux='rusanov' is built yet");
+  if (cfg_.flux < 0 || cfg_.flux > 2)
+    throw std::runtime_error("pypde_b200: FLUX must be 0 (rusanov), 1 (roe) or 2 (osher)");
   choose_block_shapes(cfg_);
   ensure_context();
   const DriverApi &d = driver();
@@ -511,7 +511,7 @@ void Solver::step_async() {
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
     launch(mod_->k_dg, (unsigned)nblocks, block, smem, args, "k_dg");
   }
-  if (cfg_.useF) {
+  if (cfg_.useF && cfg_.flux == 0) {
     long total = ncellw_ * 2 * nd * ipow(N, nd - 1);
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
     launch(mod_->k_wavespeeds, grid_for(total, 128), 128, 0, args, "k_wavespeeds");

@@ -160,4 +160,21 @@ def solver_cases():
     c['reactive2d_disc_N3_stiff'] = dict(system='reactive_euler', Q0=reactive_disc((12, 12)),
                                          tf=0.02, L=[1., 1.], order=3,
                                          bts=['transitive', 'transitive'], stiff=True)
+    # Roe and Osher fluxes (fluxes.cpp:20-70)
+    c['euler1d_smooth_N3_osher'] = dict(system='euler', Q0=euler_smooth((48, )), tf=0.02, L=[1.],
+                                        order=3, bts=['periodic'], flux='osher')
+    c['euler2d_smooth_N2_roe'] = dict(system='euler', Q0=euler_smooth((16, 12)), tf=0.03,
+                                      L=[1., 1.], order=2, bts=['periodic', 'transitive'],
+                                      flux='roe')
+    c['sod_short_N2_osher'] = dict(system='euler', Q0=sod(100), tf=0.02, L=[1.], order=2,
+                                   bts=['transitive'], flux='osher')
+    c['ns1d_smooth_N2_osher'] = dict(system='navier_stokes', Q0=ns_smooth((32, )), tf=0.01,
+                                     L=[1.], order=2, bts=['periodic'], second_order=True,
+                                     flux='osher')
+    # BASELINE config 3 at reduced size: reactive Euler, stiff Newton predictor, Osher flux
+    c['reactive2d_disc_N3_stiff_osher'] = dict(system='reactive_euler',
+                                               Q0=reactive_disc((10, 10)), tf=0.02,
+                                               L=[1., 1.], order=3,
+                                               bts=['transitive', 'transitive'], stiff=True,
+                                               flux='osher')
     return c

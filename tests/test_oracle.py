@@ -41,7 +41,8 @@ def test_weno_known_answer_from_survey():
 
 # sod_N2 (102 steps) and the 2-D stiff cases (per-cell Python loops) are left to the GPU suite
 CASES = [k for k in cases.solver_cases()
-         if k not in ('sod_N2', 'advect_nc_2d_N2_stiff', 'reactive2d_disc_N3_stiff')]
+         if k not in ('sod_N2', 'advect_nc_2d_N2_stiff', 'reactive2d_disc_N3_stiff',
+                      'reactive2d_disc_N3_stiff_osher')]
 
 
 def run_oracle(c):
@@ -49,7 +50,8 @@ def run_oracle(c):
     s = SY.SYSTEMS[c['system']](ndim)
     ret, n = O.pde_solver(c['Q0'], c['tf'], c['L'], s['F'], s['B'], s['S'], bts_int(c['bts']),
                           order=c['order'], ndt=1, second_order=s['second_order'],
-                          stiff=c.get('stiff', False))
+                          stiff=c.get('stiff', False),
+                          flux=R.FLUXES[c.get('flux', 'rusanov')])
     return ret[0], n
 
 

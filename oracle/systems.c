@@ -85,3 +85,24 @@
 #define SYS_B advect_nc_3d_B
 #define SYS_S advect_nc_3d_S
 #include "../pypde_b200/systems/systems_src.h"
+#undef SYS_NDIM
+#undef SYS_F
+#undef SYS_B
+#undef SYS_S
+#undef SYS_ADVECT_NC
+
+#define SYS_GPR
+#define SYS_NDIM 1
+#define SYS_F gpr_1d_F
+#define SYS_B gpr_1d_B
+#define SYS_S gpr_1d_S
+#include "../pypde_b200/systems/systems_src.h"
+#undef SYS_NDIM
+#undef SYS_F
+#undef SYS_B
+#undef SYS_S
+#define SYS_NDIM 2
+#define SYS_F gpr_2d_F
+#define SYS_B gpr_2d_B
+#define SYS_S gpr_2d_S
+#include "../pypde_b200/systems/systems_src.h"

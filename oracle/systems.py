@@ -132,7 +132,79 @@ def advect_nc(ndim):
     return dict(F=F, B=B, S=S, V=3, second_order=False)
 
 
+def gpr(ndim):
+    """reference tests/gpr/system.py with params.py (stiffened gas, pINF = 0)."""
+    G_, CV, CS2, CA2, MU, PR, RHO0 = 1.4, 2.5, 25., 25., 2e-2, 0.75, 1.
+    P0 = 1. / G_
+    KAPPA = MU * G_ * CV / PR
+    T0 = P0 / (RHO0 * (G_ - 1.) * CV)
+    TAU1 = 6. * MU / (RHO0 * CS2)
+    TAU2 = KAPPA * RHO0 / (T0 * CA2)
+
+    def unpack(Q):
+        r = Q[..., 0]
+        ir = 1. / r
+        E = Q[..., 1] * ir
+        v = Q[..., 2:5] * ir[..., None]
+        A = Q[..., 5:14].reshape(Q.shape[:-1] + (3, 3))
+        J = Q[..., 14:17] * ir[..., None]
+        Gm = np.einsum('...ki,...kj->...ij', A, A)
+        tr3 = (Gm[..., 0, 0] + Gm[..., 1, 1] + Gm[..., 2, 2]) / 3.
+        dev = Gm - tr3[..., None, None] * np.eye(3)
+        devG2 = (dev * dev).sum(axis=(-1, -2))
+        psi = CS2 * np.einsum('...ik,...kj->...ij', A, dev)
+        E3 = (v * v).sum(axis=-1) / 2.
+        E1 = E - E3 - CS2 / 4. * devG2 - CA2 / 2. * (J * J).sum(axis=-1)
+        p = E1 * r * (G_ - 1.)
+        T = p / (r * (G_ - 1.) * CV)
+        return r, E, v, A, J, psi, p, T
+
+    def F(Q, dQ, d):
+        r, E, v, A, J, psi, p, T = unpack(Q)
+        sig = -r[..., None, None] * np.einsum('...ki,...kj->...ij', A, psi)
+        vd = v[..., d]
+        rvd = r * vd
+        out = np.zeros_like(Q)
+        out[..., 0] = rvd
+        out[..., 1] = rvd * E + p * vd
+        out[..., 2:5] = rvd[..., None] * v
+        out[..., 2 + d] += p
+        out[..., 1] -= (sig[..., d, :] * v).sum(axis=-1)
+        out[..., 2:5] -= sig[..., d, :]
+        Av = np.einsum('...ik,...k->...i', A, v)
+        for i in range(3):
+            out[..., 5 + 3 * i + d] = Av[..., i]
+        out[..., 1] += CA2 * J[..., d] * T
+        out[..., 14:17] = rvd[..., None] * J
+        out[..., 14 + d] += T
+        return out
+
+    def B(Q, d):
+        v = Q[..., 2:5] / Q[..., 0:1]
+        out = np.zeros(Q.shape + (17, ))
+        for i in range(5, 14):
+            out[..., i, i] = v[..., d]
+        for k in range(3):
+            out[..., 5 + d, 5 + d + k] -= v[..., k]
+            out[..., 8 + d, 8 + d + k] -= v[..., k]
+            out[..., 11 + d, 11 + d + k] -= v[..., k]
+        return out
+
+    def S(Q):
+        r, E, v, A, J, psi, p, T = unpack(Q)
+        det = np.linalg.det(A)
+        th1 = 3. * det**(5. / 3.) / (CS2 * TAU1)
+        th2 = 1. / (CA2 * TAU2 * (r / RHO0) * (T0 / T))
+        out = np.zeros_like(Q)
+        out[..., 5:14] = -psi.reshape(Q.shape[:-1] + (9, )) * th1[..., None]
+        out[..., 14:17] = -r[..., None] * (CA2 * J) * th2[..., None]
+        return out
+
+    return dict(F=F, B=B, S=S, V=17, second_order=False)
+
+
 SYSTEMS = {
+    'gpr': gpr,
     'euler': euler,
     'reactive_euler': reactive_euler,
     'navier_stokes': navier_stokes,

@@ -16,6 +16,7 @@ SYSTEMS = {
     'reactive_euler': (lambda nd: 3 + nd, True, False, True, False),
     'navier_stokes': (lambda nd: 5, True, False, False, True),
     'advect_nc': (lambda nd: 3, True, True, True, False),
+    'gpr': (lambda nd: 17, True, True, True, False),
 }
 
 

@@ -19,6 +19,8 @@
  *                   docs/pages/example_pdes.rst:35-61
  *   NAVIER_STOKES   tests/navier_stokes/system.py:22-52
  *   ADVECT_NC       a small non-conservative + source system for the B/S paths
+ *   GPR             tests/gpr/system.py + misc/*.py + params.py (Godunov-Peshkov-Romenski
+ *                   continuum model, V = 17, stiffened-gas EOS with pINF = 0)
  */
 #ifndef PDE_FN
 #ifdef __CUDACC__
@@ -167,5 +169,149 @@ PDE_FN void SYS_S(double *out, const double *Q) {
   out[0] = -0.5 * (Q[0] - 1.);
   out[1] = 0.3 * Q[2] - 0.2 * Q[1];
   out[2] = -0.1 * Q[2] * Q[0];
+}
+#endif
+
+#if defined(SYS_GPR)
+/* Q = [rho, rho E, rho v(3), A(3x3 row-major), rho J(3)], V = 17.
+ * Parameters of reference tests/gpr/params.py. */
+#define GPR_G 1.4
+#define GPR_CV 2.5
+#define GPR_CS2 25.
+#define GPR_CA2 25.
+#define GPR_MU 2e-2
+#define GPR_PR 0.75
+#define GPR_RHO0 1.
+#define GPR_P0 (1. / GPR_G)
+#define GPR_KAPPA (GPR_MU * GPR_G * GPR_CV / GPR_PR)
+#define GPR_T0 (GPR_P0 / (GPR_RHO0 * (GPR_G - 1.) * GPR_CV))
+#define GPR_TAU1 (6. * GPR_MU / (GPR_RHO0 * GPR_CS2))
+#define GPR_TAU2 (GPR_KAPPA * GPR_RHO0 / (GPR_T0 * GPR_CA2))
+
+#ifndef GPR_HELPERS
+#define GPR_HELPERS
+#ifdef __CUDACC__
+#define GPR_INL static __device__ inline
+#else
+#define GPR_INL static inline
+#endif
+/* psi = dE/dA = cs^2 A dev(A^T A); returns sum(dev(G)^2) for E_2A (misc/state.py, eos.py) */
+GPR_INL double gpr_psi(const double *A, double *psi) {
+  double G[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double acc = 0.;
+      for (int k = 0; k < 3; k++)
+        acc += A[k * 3 + i] * A[k * 3 + j];
+      G[i * 3 + j] = acc;
+    }
+  double tr3 = (G[0] + G[4] + G[8]) / 3.;
+  G[0] -= tr3;
+  G[4] -= tr3;
+  G[8] -= tr3;
+  double s2 = 0.;
+  for (int i = 0; i < 9; i++)
+    s2 += G[i] * G[i];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double acc = 0.;
+      for (int k = 0; k < 3; k++)
+        acc += A[i * 3 + k] * G[k * 3 + j];
+      psi[i * 3 + j] = GPR_CS2 * acc;
+    }
+  return s2;
+}
+/* pressure and temperature of the state (misc/state.py, mg.py) */
+GPR_INL void gpr_pT(double r, double E, const double *v, double devG2, const double *J, double *p,
+                    double *T) {
+  double E3 = (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / 2.;
+  double E2A = GPR_CS2 / 4. * devG2;
+  double E2J = GPR_CA2 / 2. * (J[0] * J[0] + J[1] * J[1] + J[2] * J[2]);
+  double E1 = E - E3 - E2A - E2J;
+  *p = E1 * r * (GPR_G - 1.);
+  *T = *p / (r * (GPR_G - 1.) * GPR_CV);
+}
+#endif
+
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  double r = Q[0];
+  double ir = 1. / r;
+  double E = Q[1] * ir;
+  double v[3], J[3], psi[9], sig[9];
+  const double *A = Q + 5;
+  for (int i = 0; i < 3; i++) {
+    v[i] = Q[2 + i] * ir;
+    J[i] = Q[14 + i] * ir;
+  }
+  double devG2 = gpr_psi(A, psi);
+  double p, T;
+  gpr_pT(r, E, v, devG2, J, &p, &T);
+  /* sigma = -rho A^T psi */
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double acc = 0.;
+      for (int k = 0; k < 3; k++)
+        acc += A[k * 3 + i] * psi[k * 3 + j];
+      sig[i * 3 + j] = -r * acc;
+    }
+  double vd = v[d];
+  double rvd = r * vd;
+  for (int i = 0; i < 17; i++)
+    out[i] = 0.;
+  out[0] = rvd;
+  out[1] = rvd * E + p * vd;
+  for (int i = 0; i < 3; i++)
+    out[2 + i] = rvd * v[i];
+  out[2 + d] += p;
+  out[1] -= sig[d * 3 + 0] * v[0] + sig[d * 3 + 1] * v[1] + sig[d * 3 + 2] * v[2];
+  for (int i = 0; i < 3; i++)
+    out[2 + i] -= sig[d * 3 + i];
+  for (int i = 0; i < 3; i++)
+    out[5 + 3 * i + d] = A[i * 3 + 0] * v[0] + A[i * 3 + 1] * v[1] + A[i * 3 + 2] * v[2];
+  out[1] += GPR_CA2 * J[d] * T;
+  for (int i = 0; i < 3; i++)
+    out[14 + i] = rvd * J[i];
+  out[14 + d] += T;
+  (void)dQ;
+}
+PDE_FN void SYS_B(double *out, const double *Q, int d) {
+  double ir = 1. / Q[0];
+  double v[3];
+  for (int i = 0; i < 3; i++)
+    v[i] = Q[2 + i] * ir;
+  for (int i = 0; i < 17 * 17; i++)
+    out[i] = 0.;
+  for (int i = 5; i < 14; i++)
+    out[i * 17 + i] = v[d];
+  /* ret[5+d, 5+d:8+d] -= v etc., exactly as the reference example's slices */
+  for (int k = 0; k < 3; k++) {
+    out[(5 + d) * 17 + 5 + d + k] -= v[k];
+    out[(8 + d) * 17 + 8 + d + k] -= v[k];
+    out[(11 + d) * 17 + 11 + d + k] -= v[k];
+  }
+}
+PDE_FN void SYS_S(double *out, const double *Q) {
+  double r = Q[0];
+  double ir = 1. / r;
+  double E = Q[1] * ir;
+  double v[3], J[3], psi[9];
+  const double *A = Q + 5;
+  for (int i = 0; i < 3; i++) {
+    v[i] = Q[2 + i] * ir;
+    J[i] = Q[14 + i] * ir;
+  }
+  double devG2 = gpr_psi(A, psi);
+  double p, T;
+  gpr_pT(r, E, v, devG2, J, &p, &T);
+  double det = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) +
+               A[2] * (A[3] * A[7] - A[4] * A[6]);
+  double th1 = 3. * pow(det, 5. / 3.) / (GPR_CS2 * GPR_TAU1);
+  double th2 = 1. / (GPR_CA2 * GPR_TAU2 * (r / GPR_RHO0) * (GPR_T0 / T));
+  for (int i = 0; i < 5; i++)
+    out[i] = 0.;
+  for (int i = 0; i < 9; i++)
+    out[5 + i] = -psi[i] * th1;
+  for (int i = 0; i < 3; i++)
+    out[14 + i] = -r * (GPR_CA2 * J[i]) * th2;
 }
 #endif

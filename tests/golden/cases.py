@@ -108,6 +108,28 @@ def reactive_disc(shape, smooth=False):
     return reactive_state(rho, p, [np.zeros(shape)] * len(shape), lam)
 
 
+def gpr_state(rho, p, vel):
+    """reference tests/gpr/misc/utils.py Cvec with A = rho^(1/3) I, J = 0
+    (E = p/((g-1) rho) + v.v/2: the distortion energy of A = c I vanishes)."""
+    rho = np.asarray(rho, dtype=float)
+    Q = np.zeros(rho.shape + (17, ))
+    Q[..., 0] = rho
+    Q[..., 1] = p / (G - 1) + rho * sum(np.asarray(v) * v for v in vel) / 2
+    for i, v in enumerate(vel):
+        Q[..., 2 + i] = rho * v
+    for i in range(3):
+        Q[..., 5 + 4 * i] = rho**(1. / 3.)
+    return Q
+
+
+def gpr_disc(shape, smooth=True):
+    """BASELINE config 4 IC: (rho, p) = (4, 4/g) in (2, 2/g)."""
+    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape)))
+    s = 0.5 * (1 - np.tanh((r - 0.25) / 0.1)) if smooth else (r < 0.25).astype(float)
+    rho = 2.0 + 2.0 * s
+    return gpr_state(rho, rho / G, [0.1 * np.ones(shape), np.zeros(shape), np.zeros(shape)])
+
+
 def weno_kat_input():
     return np.array([1, 2, 4, 7, 11, 16, 22.]).reshape(7, 1)
 
@@ -171,6 +193,11 @@ def solver_cases():
     c['ns1d_smooth_N2_osher'] = dict(system='navier_stokes', Q0=ns_smooth((32, )), tf=0.01,
                                      L=[1.], order=2, bts=['periodic'], second_order=True,
                                      flux='osher')
+    # BASELINE config 4 at reduced size: GPR model (V = 17, F + B + S), stiff, order 2
+    c['gpr1d_N2_stiff'] = dict(system='gpr', Q0=gpr_disc((24, )), tf=0.004, L=[1.], order=2,
+                               bts=['transitive'], stiff=True)
+    c['gpr2d_N2_stiff'] = dict(system='gpr', Q0=gpr_disc((8, 8)), tf=0.006, L=[1., 1.], order=2,
+                               bts=['transitive', 'transitive'], stiff=True)
     # BASELINE config 3 at reduced size: reactive Euler, stiff Newton predictor, Osher flux
     c['reactive2d_disc_N3_stiff_osher'] = dict(system='reactive_euler',
                                                Q0=reactive_disc((10, 10)), tf=0.02,

@@ -42,7 +42,7 @@ def test_weno_known_answer_from_survey():
 # sod_N2 (102 steps) and the 2-D stiff cases (per-cell Python loops) are left to the GPU suite
 CASES = [k for k in cases.solver_cases()
          if k not in ('sod_N2', 'advect_nc_2d_N2_stiff', 'reactive2d_disc_N3_stiff',
-                      'reactive2d_disc_N3_stiff_osher')]
+                      'reactive2d_disc_N3_stiff_osher', 'gpr2d_N2_stiff')]
 
 
 def run_oracle(c):

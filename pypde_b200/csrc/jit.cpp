@@ -173,7 +173,9 @@ void choose_block_shapes(KernelConfig &c) {
     throw std::runtime_error("pypde_b200: order too high for this ndim (N^(ndim+1) > 1024)");
   // k_dg: NT threads per cell; (2+ndim)*NT*V doubles of shared memory per cell
   const size_t sm_cell = (size_t)(2 + c.ndim) * NT * c.V * 8;
-  int cpb = 256 / NT;
+  // one warp per block measured fastest (B200, 2-D Euler N=3: 4.3 ms vs 5.2 ms with
+  // 9 cells / 243 threads): short blocks do not idle at the per-iteration barriers
+  int cpb = 32 / NT;
   if (cpb < 1)
     cpb = 1;
   while (cpb > 1 && cpb * sm_cell > 64 * 1024)
@@ -196,6 +198,15 @@ void choose_block_shapes(KernelConfig &c) {
   while (wpb > 1 && wpb * sm_warp > 96 * 1024)
     wpb--;
   c.stiff_wpb = wpb;
+  // tuning overrides (experiments)
+  if (const char *e = getenv("PYPDE_B200_WS_BLOCK"))
+    c.ws_block = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_WS_MINBLOCKS"))
+    c.ws_minblocks = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_DG_CPB"))
+    c.dg_cpb = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_FACES_FPB"))
+    c.faces_fpb = atoi(e);
 }
 
 std::vector<std::string> specialisation_defines(const KernelConfig &c) {
@@ -217,7 +228,9 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_EIG_QR_ONLY", getenv("PYPDE_B200_EIG_QR_ONLY") ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb),
-          kv("PDE_STIFF_WPB", c.stiff_wpb)};
+          kv("PDE_STIFF_WPB", c.stiff_wpb),
+          kv("PDE_WS_BLOCK", c.ws_block),
+          kv("PDE_WS_MINBLOCKS", c.ws_minblocks)};
   // tuning experiments: PYPDE_B200_EXTRA_DEFINES="PDE_X=1;PDE_Y=0"
   if (const char *e = getenv("PYPDE_B200_EXTRA_DEFINES")) {
     std::string all(e);

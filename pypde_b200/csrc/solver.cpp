@@ -514,7 +514,8 @@ void Solver::step_async() {
   if (cfg_.useF && cfg_.flux == 0) {
     long total = ncellw_ * 2 * nd * ipow(N, nd - 1);
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
-    launch(mod_->k_wavespeeds, grid_for(total, 128), 128, 0, args, "k_wavespeeds");
+    launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, 0, args,
+           "k_wavespeeds");
   }
   if (cfg_.useF || cfg_.useB) {
     const int NP = N * ipow(N, nd - 1);

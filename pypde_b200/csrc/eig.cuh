@@ -642,8 +642,14 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
     *path = 0;
   if (guess)
     guess->valid = 0;
-  balance<n>(a);
-  return spectral_radius_qr<n>(a);
+  // cold path: only here does the matrix need an address (the QR iteration indexes
+  // it dynamically); copying with static indices keeps the caller's `a` in registers
+  double tmp[n * n];
+#pragma unroll
+  for (int i = 0; i < n * n; i++)
+    tmp[i] = a[i];
+  balance<n>(tmp);
+  return spectral_radius_qr<n>(tmp);
 }
 
 // ---------------------------------------------------------------------------

@@ -294,9 +294,19 @@ def main():
     dom = max(kt, key=lambda k_: kt[k_][0])
     dom_ms = kt[dom][0] / kt[dom][1]            # average launch duration
     dom_gbs = kb.get(dom, 0.) / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')
+    if n == 2048 and os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        if dom in tj.get('kernels', {}):
+            traffic = tj['kernels'][dom]['dram_bytes']
+            traffic_src = 'profiles/r1_ncu_traffic.json (ncu --set full, dram__bytes_read+write)'
     roofline = {
         'kernel': dom, 'bound': 'hbm', 'achieved': dom_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-        'frac': dom_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+        'frac': dom_gbs / hbm_peak, 'traffic': traffic, 'traffic_source': traffic_src,
+        'algorithmic_bytes_per_launch': kb.get(dom), 'peak_source': peak_src,
         'avg_launch_ms': dom_ms, 'share_of_step': kt[dom][0] / P / step_ms_prof,
         'note': ('%s is FP64-pipe bound (finite-difference Jacobians + eigen-solves per face '
                  'node), not HBM bound; fp64 figures below' % dom),

@@ -94,7 +94,10 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
     do {
       for (l = nn; l > 0; l--) {
         s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
-        if (s == 0.)
+        // both diagonal entries negligible against the matrix (zero, or denormal
+        // leftovers such as a fully burnt mass fraction ~1e-308): measure the
+        // subdiagonal against the norm instead — a backward error of eps ||A||
+        if (s <= DBL_EPS * anorm)
           s = anorm;
         if (fabs(A_(l, l - 1)) <= DBL_EPS * s) {
           A_(l, l - 1) = 0.;
@@ -743,7 +746,10 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
     do {
       for (l = nn; l > 0; l--) {
         s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
-        if (s == 0.)
+        // both diagonal entries negligible against the matrix (zero, or denormal
+        // leftovers such as a fully burnt mass fraction ~1e-308): measure the
+        // subdiagonal against the norm instead — a backward error of eps ||A||
+        if (s <= DBL_EPS * anorm)
           s = anorm;
         if (fabs(A_(l, l - 1)) <= DBL_EPS * s) {
           A_(l, l - 1) = 0.;

@@ -192,8 +192,8 @@ void choose_block_shapes(KernelConfig &c) {
   while (fpb > 1 && (size_t)fpb * NP * sm_pt > 48 * 1024)
     fpb--;
   c.faces_fpb = fpb;
-  // k_dg_stiff: one warp per cell, (3+ndim) n doubles of shared memory per warp
-  const size_t sm_warp = (size_t)(3 + c.ndim) * NT * c.V * 8;
+  // k_dg_stiff: one warp per cell, (6+ndim) n doubles of shared memory per warp
+  const size_t sm_warp = (size_t)(6 + c.ndim) * NT * c.V * 8;
   int wpb = 4;
   while (wpb > 1 && wpb * sm_warp > 96 * 1024)
     wpb--;

@@ -206,13 +206,13 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   if (cfg_.stiff) {
     // one warp per cell; global workspace per warp (kernels.cuh: NK_WORK)
     const size_t n = (size_t)N * Nd * V;
-    const size_t nk_work = 5 * n + 41 * n + 10 * n + 42 * 41 + 6 * 41;
+    const size_t nk_work = 41 * n + 10 * n + 42 * 41 + 6 * 41;
     stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
-    const size_t smem_warp = (3 + nd) * n * D;
+    const size_t smem_warp = (6 + nd) * n * D;
     if (smem_warp > 220 * 1024)
       throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
     long blocks = (ncellw_ + stiff_wpb_ - 1) / stiff_wpb_;
-    long cap = (long)sms_ * 4;
+    long cap = (long)sms_ * 8;
     stiff_blocks_ = blocks < cap ? blocks : cap;
     stiff_work_.alloc((size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D);
     if (stiff_wpb_ * smem_warp > 48 * 1024)
@@ -498,7 +498,7 @@ void Solver::step_async() {
     launch(mod_->k_dt, 1, 1, 0, args, "k_dt");
   }
   if (cfg_.stiff) {
-    const size_t smem = (size_t)stiff_wpb_ * (3 + nd) * N * Nd * V * sizeof(double);
+    const size_t smem = (size_t)stiff_wpb_ * (6 + nd) * N * Nd * V * sizeof(double);
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p, &stiff_work_.p};
     launch(mod_->k_dg_stiff, (unsigned)stiff_blocks_, 32 * stiff_wpb_, smem, args, "k_dg_stiff");
   } else {

@@ -86,7 +86,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None

@@ -15,17 +15,19 @@ holds one of
 
 and the library links it into the hand-written kernels with nvJitLink.
 
-Python functions must be written in numba-CUDA's device subset ("device
-style"): scalar arithmetic on the argument arrays, results written into the
-leading `out` argument, no array allocation:
+Python functions come in two styles:
 
-    F(out, Q, d)          or  F(out, Q, dQ, d)      (first / second order)
-    B(out, Q, d)                                   (out is V x V)
-    S(out, Q)
+* reference style — exactly what the reference accepts (pypde/solvers.py:30-55):
+  ``F(Q)``, ``F(Q, d)``, ``F(Q, dQ, d)``, ``B(Q)``, ``B(Q, d)``, ``S(Q)`` returning
+  arrays.  numba's CUDA target cannot allocate or return arrays (SURVEY.md
+  §7.3-H2), so these are lowered by symbolic tracing to CUDA source
+  (pypde_b200/tracing.py);
+* device style — scalar code writing into a leading `out` argument, lowered
+  through numba's CUDA target to LTO-IR:
+  ``F(out, Q, d)`` / ``F(out, Q, dQ, d)``, ``B(out, Q, d)``, ``S(out, Q)``.
 
-A reference-style function (``F(Q, d) -> ndarray``) is recognised by its arity
-and rejected with a message explaining the rewrite, since numba's CUDA target
-cannot allocate or return arrays.
+A three-parameter F is ambiguous (``F(Q, dQ, d)`` or ``F(out, Q, d)``): it is
+traced as reference style first; if it returns nothing it is device style.
 """
 import ctypes
 from ctypes import POINTER, Structure, c_char_p, c_int, c_size_t, c_void_p
@@ -113,11 +115,9 @@ def lower_python(func, kind, ndim, V):
     n = nargs(func)
     if n not in _device_style_arity(kind):
         raise TypeError(
-            'pypde_b200: %s has %d parameters. GPU user functions take the '
-            'output array first — F(out, Q, d) / F(out, Q, dQ, d), '
-            'B(out, Q, d), S(out, Q) — and use scalar arithmetic only: '
-            "numba's CUDA target cannot allocate or return arrays, so the "
-            'reference style F(Q, d) -> ndarray cannot be lowered to the GPU.' %
+            'pypde_b200: %s has %d parameters; device-style GPU user functions take the '
+            'output array first — F(out, Q, d) / F(out, Q, dQ, d), B(out, Q, d), '
+            'S(out, Q) — and use scalar arithmetic only.' %
             (getattr(func, '__name__', kind), n))
 
     dev = cuda.jit(device=True, inline=True)(func)
@@ -189,12 +189,37 @@ def lower_python(func, kind, ndim, V):
                           getattr(func, '__name__', 'user_' + kind))
 
 
+REFERENCE_ARITY = {'F': (1, 2, 3), 'B': (1, 2), 'S': (1, )}
+
+
+def lower_reference_style(func, kind, ndim, V):
+    """Reference-style function -> CUDA source by symbolic tracing."""
+    from pypde_b200.tracing import trace_function
+    src, second_order = trace_function(func, kind, ndim, V)
+    fn = CudaSource(src, getattr(func, '__name__', 'user_' + kind))
+    fn.second_order = second_order
+    fn.style = 'reference'
+    return fn
+
+
 def _lower(func, kind, ndim, V):
     if func is None:
         return None
     if isinstance(func, DeviceFunction):
         return func
-    return lower_python(func, kind, ndim, V)
+    from pypde_b200.utils import nargs
+    n = nargs(func)
+    if n in REFERENCE_ARITY[kind]:
+        try:
+            return lower_reference_style(func, kind, ndim, V)
+        except Exception as err:
+            if n not in _device_style_arity(kind):
+                raise TypeError('pypde_b200: cannot lower %s for the GPU: %s' %
+                                (getattr(func, '__name__', kind), err)) from err
+    fn = lower_python(func, kind, ndim, V)
+    fn.second_order = kind == 'F' and n == 4
+    fn.style = 'device'
+    return fn
 
 
 def generate_cfuncs(F, B, S, ndim, V):

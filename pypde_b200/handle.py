@@ -82,7 +82,8 @@ class Solver:
                                           self.dX.ctypes.data_as(POINTER(c_double)), cfl,
                                           bt.ctypes.data_as(POINTER(c_int)), int(stiff),
                                           FLUXES[flux], order, self.V,
-                                          int(_is_second_order(F))), 'pypde_b200_create')
+                                          int(_is_second_order(self._fns[0]))),
+               'pypde_b200_create')
         self.ncell = int(nX.prod())
         self._bound = None
 

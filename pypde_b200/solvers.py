@@ -5,9 +5,10 @@ Argument names, defaults, marshalling and return shapes follow
 pypde/solvers.py:13-25,177-214 and :217-244.  Differences, all forced by the
 GPU target:
 
-* F, B, S are device-style Python functions or `DeviceFunction`/`CudaSource`
-  objects (see pypde_b200/cfuncs.py); `secondOrder` is still decided by F's
-  arity (reference solvers.py:196), i.e. 4 parameters in device style.
+* F, B, S are lowered to device code (pypde_b200/cfuncs.py): reference-style
+  Python functions by symbolic tracing, device-style ones through numba's CUDA
+  target, or given directly as `CudaSource`; `secondOrder` is still decided by
+  F's arity (reference solvers.py:196).
 * a failure inside the library raises RuntimeError (the reference's C ABI has
   no error channel; a CUDA library cannot silently continue).
 """
@@ -24,11 +25,9 @@ FLUXES = {'rusanov': 0, 'roe': 1, 'osher': 2}
 
 
 def _is_second_order(F):
-    if F is None:
-        return False
-    if isinstance(F, DeviceFunction):
-        return bool(getattr(F, 'second_order', False))
-    return nargs(F) == 4
+    """reference solvers.py:196 decides by F's arity; here the lowered function
+    carries the answer (reference style: 3 parameters; device style: 4)."""
+    return bool(getattr(F, 'second_order', False)) if F is not None else False
 
 
 def pde_solver(Q0,
@@ -59,11 +58,11 @@ def pde_solver(Q0,
     useB = B is not None
     useS = S is not None
 
-    secondOrder = _is_second_order(F)
-
     print('compiling functions...')
 
     _F, _B, _S = generate_cfuncs(F, B, S, ndim, V)
+
+    secondOrder = _is_second_order(_F)
 
     solver = create_solver()
 

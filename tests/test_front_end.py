@@ -56,11 +56,13 @@ def test_second_order_by_arity():
     assert nargs(F_euler1d) == 3
 
 
-def test_reference_style_function_is_rejected_with_guidance():
+def test_reference_style_function_is_traced():
     def F_ref_style(Q, d):
-        return Q
+        return Q * (1.0 + d)
+    F = cfuncs._lower(F_ref_style, 'F', 2, 3)
+    assert F.kind == cfuncs.CUDA_SOURCE and F.style == 'reference' and b'user_F' in F.image
     with pytest.raises(TypeError, match='output array first'):
-        cfuncs.lower_python(F_ref_style, 'F', 1, 3)
+        cfuncs.lower_python(F_ref_style, 'F', 1, 3)     # not device style
 
 
 def test_numba_lowering_links_into_kernels():

@@ -170,6 +170,54 @@ def test_numba_user_function_matches_cuda_source(golden):
     assert rel_linf(out[0], golden['solver']['euler2d_smooth_N3']) < 1e-10
 
 
+# ------------------------------------- reference-style user functions (traced)
+def F_euler_reference_style(Q):
+    """as reference pypde/tests/euler/system.py: F(Q) -> ndarray"""
+    from numpy import array
+    g = 1.4
+    r = Q[0]
+    E = Q[1] / r
+    v = Q[2] / r
+    e = E - v**2 / 2
+    p = (g - 1) * r * e
+    return array([r * v, r * E * v + p * v, r * v**2 + p])
+
+
+def F_ns_reference_style(Q, dQ, d):
+    """as reference pypde/tests/navier_stokes/system.py: F(Q, dQ, d) -> ndarray"""
+    from numpy import dot, eye, zeros
+    mu = 1e-2
+    ret = zeros(5)
+    r = Q[0]
+    E = Q[1] / r
+    v = Q[2:5] / r
+    dv_dx = (dQ[0, 2:5] - dQ[0, 0] * v) / r
+    dv = zeros((3, 3))
+    dv[0] = dv_dx
+    p = r * 0.4 * (E - dot(v, v) / 2)
+    sig = mu * (dv + dv.T - 2 / 3 * (dv[0, 0] + dv[1, 1] + dv[2, 2]) * eye(3))
+    vd = v[d]
+    ret[0] = r * vd
+    ret[1] = r * vd * E + p * vd
+    ret[2:5] = r * vd * v
+    ret[2 + d] += p
+    ret[1] -= dot(sig[d], v)
+    ret[2:5] -= sig[d]
+    return ret
+
+
+@pytest.mark.parametrize('name,F', [('euler1d_smooth_N3', F_euler_reference_style),
+                                    ('ns2d_smooth_N2', F_ns_reference_style)])
+def test_reference_style_functions_through_pde_solver(golden, name, F):
+    """The reference's calling convention end to end: a Python F returning an
+    ndarray goes straight into pde_solver (traced to CUDA source, cfuncs.py)."""
+    c = cases.solver_cases()[name]
+    Q0 = c['Q0'].copy()
+    out = pypde_b200.pde_solver(Q0, c['tf'], c['L'], F=F, boundaryTypes=c['bts'],
+                                order=c['order'], ndt=1, stiff=False)
+    assert rel_linf(out[0], golden['solver'][name]) < parity_tolerance(golden['solver'], name)
+
+
 # ------------------------------------------------- size-independent properties
 def test_constant_state_is_preserved_exactly():
     F, B, S, V = cuda_sources('euler', 2)

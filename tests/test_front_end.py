@@ -52,7 +52,12 @@ def S_lin(out, Q):
 
 
 def test_second_order_by_arity():
-    assert not _is_second_order(F_euler1d) and _is_second_order(F_second)
+    """reference solvers.py:196: secondOrder = (F takes dQ); the lowered function
+    carries it (device style: 4 parameters, reference style: 3)."""
+    F1, _, _ = cfuncs.generate_cfuncs(F_euler1d, None, None, 1, 3)
+    F2, _, _ = cfuncs.generate_cfuncs(F_second, None, None, 1, 1)
+    assert not _is_second_order(F1) and _is_second_order(F2)
+    assert not _is_second_order(None)
     assert nargs(F_euler1d) == 3
 
 

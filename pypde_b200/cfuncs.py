@@ -209,14 +209,24 @@ def _lower(func, kind, ndim, V):
         return func
     from pypde_b200.utils import nargs
     n = nargs(func)
+    trace_err = None
     if n in REFERENCE_ARITY[kind]:
         try:
             return lower_reference_style(func, kind, ndim, V)
         except Exception as err:
+            trace_err = err
             if n not in _device_style_arity(kind):
                 raise TypeError('pypde_b200: cannot lower %s for the GPU: %s' %
                                 (getattr(func, '__name__', kind), err)) from err
-    fn = lower_python(func, kind, ndim, V)
+    try:
+        fn = lower_python(func, kind, ndim, V)
+    except Exception as err:
+        if trace_err is None:
+            raise
+        raise TypeError('pypde_b200: cannot lower %s for the GPU.\n  as a reference-style '
+                        'function (traced): %s\n  as a device-style function (numba CUDA): %s' %
+                        (getattr(func, '__name__', kind), trace_err,
+                         str(err).splitlines()[0])) from err
     fn.second_order = kind == 'F' and n == 4
     fn.style = 'device'
     return fn

@@ -17,7 +17,9 @@ Supported inside user functions: indexing / slicing / arithmetic on arrays,
 `where`, `**` (small integer powers become products, as numba emits them),
 helper functions (plain or `@njit`) called with array or scalar arguments, and
 branches on the direction `d` or on constants.  A branch on a *data* value
-(`K0 if T > Ti else 0`) cannot be traced: use `where(T > Ti, K0, 0)`.
+(`K0 if T > Ti else 0`) cannot be traced: use `where(T > Ti, K0, 0)`.  numpy
+names must be module-level imports of the function's module (imports inside the
+function body bind the real numpy and are not seen by the tracer).
 """
 import math
 import types

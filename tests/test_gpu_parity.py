@@ -173,19 +173,18 @@ def test_numba_user_function_matches_cuda_source(golden):
 # ------------------------------------- reference-style user functions (traced)
 def F_euler_reference_style(Q):
     """as reference pypde/tests/euler/system.py: F(Q) -> ndarray"""
-    from numpy import array
     g = 1.4
     r = Q[0]
     E = Q[1] / r
     v = Q[2] / r
     e = E - v**2 / 2
     p = (g - 1) * r * e
-    return array([r * v, r * E * v + p * v, r * v**2 + p])
+    return np.array([r * v, r * E * v + p * v, r * v**2 + p])
 
 
 def F_ns_reference_style(Q, dQ, d):
     """as reference pypde/tests/navier_stokes/system.py: F(Q, dQ, d) -> ndarray"""
-    from numpy import dot, eye, zeros
+    dot, eye, zeros = np.dot, np.eye, np.zeros
     mu = 1e-2
     ret = zeros(5)
     r = Q[0]
@@ -194,7 +193,7 @@ def F_ns_reference_style(Q, dQ, d):
     dv_dx = (dQ[0, 2:5] - dQ[0, 0] * v) / r
     dv = zeros((3, 3))
     dv[0] = dv_dx
-    p = r * 0.4 * (E - dot(v, v) / 2)
+    p = r * (1.4 - 1) * (E - dot(v, v) / 2)
     sig = mu * (dv + dv.T - 2 / 3 * (dv[0, 0] + dv[1, 1] + dv[2, 2]) * eye(3))
     vd = v[d]
     ret[0] = r * vd

@@ -106,3 +106,18 @@
 #define SYS_B gpr_2d_B
 #define SYS_S gpr_2d_S
 #include "../pypde_b200/systems/systems_src.h"
+#undef SYS_NDIM
+#undef SYS_F
+#undef SYS_B
+#undef SYS_S
+#undef SYS_GPR
+
+#define SYS_BURGERS
+#define SYS_NDIM 1
+#define SYS_F burgers_1d_F
+#include "../pypde_b200/systems/systems_src.h"
+#undef SYS_NDIM
+#undef SYS_F
+#define SYS_NDIM 2
+#define SYS_F burgers_2d_F
+#include "../pypde_b200/systems/systems_src.h"

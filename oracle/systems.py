@@ -203,8 +203,17 @@ def gpr(ndim):
     return dict(F=F, B=B, S=S, V=17, second_order=False)
 
 
+def burgers(ndim):
+    def F(Q, dQ, d):
+        a = 1. - 0.4 * d
+        return a * Q * Q / 2.
+
+    return dict(F=F, B=None, S=None, V=1, second_order=False)
+
+
 SYSTEMS = {
     'gpr': gpr,
+    'burgers': burgers,
     'euler': euler,
     'reactive_euler': reactive_euler,
     'navier_stokes': navier_stokes,

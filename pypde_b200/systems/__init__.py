@@ -17,6 +17,7 @@ SYSTEMS = {
     'navier_stokes': (lambda nd: 5, True, False, False, True),
     'advect_nc': (lambda nd: 3, True, True, True, False),
     'gpr': (lambda nd: 17, True, True, True, False),
+    'burgers': (lambda nd: 1, True, False, False, False),
 }
 
 

@@ -19,6 +19,7 @@
  *                   docs/pages/example_pdes.rst:35-61
  *   NAVIER_STOKES   tests/navier_stokes/system.py:22-52
  *   ADVECT_NC       a small non-conservative + source system for the B/S paths
+ *   BURGERS         scalar conservation law (V = 1): the 1 x 1 eigen path
  *   GPR             tests/gpr/system.py + misc/*.py + params.py (Godunov-Peshkov-Romenski
  *                   continuum model, V = 17, stiffened-gas EOS with pINF = 0)
  */
@@ -169,6 +170,15 @@ PDE_FN void SYS_S(double *out, const double *Q) {
   out[0] = -0.5 * (Q[0] - 1.);
   out[1] = 0.3 * Q[2] - 0.2 * Q[1];
   out[2] = -0.1 * Q[2] * Q[0];
+}
+#endif
+
+#if defined(SYS_BURGERS)
+/* V = 1: F_d = a_d q^2 / 2 */
+PDE_FN void SYS_F(double *out, const double *Q, const double *dQ, int d) {
+  double a = 1. - 0.4 * d;
+  out[0] = a * Q[0] * Q[0] / 2.;
+  (void)dQ;
 }
 #endif
 

@@ -195,6 +195,19 @@ def solver_cases():
     c['ns1d_smooth_N2_osher'] = dict(system='navier_stokes', Q0=ns_smooth((32, )), tf=0.01,
                                      L=[1.], order=2, bts=['periodic'], second_order=True,
                                      flux='osher')
+    # edge cases: scalar system (V = 1), order 1 and 4, tiny grids, a 2-D strip one cell wide
+    c['burgers1d_N3'] = dict(system='burgers', Q0=1.5 + smooth_product((40, ))[..., None],
+                             tf=0.05, L=[1.], order=3, bts=['periodic'])
+    c['burgers2d_N2'] = dict(system='burgers', Q0=1.5 + smooth_product((12, 10))[..., None],
+                             tf=0.05, L=[1., 1.], order=2, bts=['periodic', 'transitive'])
+    c['euler1d_N1'] = dict(system='euler', Q0=euler_smooth((32, )), tf=0.02, L=[1.], order=1,
+                           bts=['periodic'])
+    c['euler1d_N4'] = dict(system='euler', Q0=euler_smooth((24, )), tf=0.02, L=[1.], order=4,
+                           bts=['transitive'])
+    c['euler1d_tiny'] = dict(system='euler', Q0=euler_smooth((3, )), tf=0.1, L=[1.], order=2,
+                             bts=['transitive'])
+    c['euler2d_strip_N2'] = dict(system='euler', Q0=euler_smooth((40, 1)), tf=0.02, L=[1., 1.],
+                                 order=2, bts=['transitive', 'transitive'])
     # BASELINE config 4 at reduced size: GPR model (V = 17, F + B + S), stiff, order 2
     c['gpr1d_N2_stiff'] = dict(system='gpr', Q0=gpr_disc((24, )), tf=0.004, L=[1.], order=2,
                                bts=['transitive'], stiff=True)

@@ -428,10 +428,13 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
         printf("t = %g\n", t);
 
       if (t >= double(pushCount + 1) / double(ndt) * tf && pushCount < ndt) {
-        solver.get_state(_ret + (size_t)pushCount * n);
+        // asynchronous: D2D on the compute stream, D2H on a copy stream, overlapping
+        // the next steps
+        solver.snapshot_async(_ret + (size_t)pushCount * n);
         pushCount += 1;
       }
       if (nan_found || std::isnan(t)) {
+        solver.drain_snapshots();
         // iterator.cpp:141-145 (rows clamped to the buffer; the loop stops here
         // instead of running on with NaNs)
         printf("NaNs found");
@@ -443,6 +446,7 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
       }
     }
     fflush(stdout);
+    solver.drain_snapshots();
     // iterator.cpp:150 and the in-place update of _u (api.cpp:18, iterator.cpp:129)
     solver.get_state(_u);
     if (ndt >= 1)

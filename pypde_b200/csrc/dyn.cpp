@@ -80,6 +80,7 @@ const DriverApi &driver() {
       B(EventRecord, "cuEventRecord");
       B(EventSynchronize, "cuEventSynchronize");
       B(EventElapsedTime, "cuEventElapsedTime");
+      B(StreamWaitEvent, "cuStreamWaitEvent");
 #undef B
       CUresult r = api.Init(0);
       if (r != CUDA_SUCCESS) {

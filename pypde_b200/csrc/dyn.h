@@ -47,6 +47,7 @@ struct DriverApi {
   CUresult (*EventRecord)(CUevent, CUstream);
   CUresult (*EventSynchronize)(CUevent);
   CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
+  CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
 };
 
 struct NvrtcApi {

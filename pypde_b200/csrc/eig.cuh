@@ -740,7 +740,7 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
     for (int j = (i > 0 ? i - 1 : 0); j < n; j++)
       anorm += fabs(A_(i, j));
   int nn = n - 1;
-  double t = 0., p = 0., q = 0., r = 0., s = 0., w, xx, yy, z;
+  double t = 0., p = 0., q = 0., r = 0., s = 0., w, xx, yy, z = 0.;
   while (nn >= 0) {
     int its = 0, l;
     do {
@@ -1021,19 +1021,13 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
   // eigenvalue (v = 0 in gas at rest: a triple zero in 3-D) the back-substituted
   // vectors can be numerically dependent; pivots below n eps |largest pivot| are
   // dropped and their coefficients set to zero (the basic solution).
-  double c[n], rhs[n], cn2[n];
+  double c[n], rhs[n];
   int cp[n];
   for (int i = 0; i < n * n; i++)
     a[i] = zz[i];
   for (int i = 0; i < n; i++) {
     rhs[i] = x[i];
     cp[i] = i;
-  }
-  for (int j = 0; j < n; j++) {
-    double sacc = 0.;
-    for (int i = 0; i < n; i++)
-      sacc += A_(i, j) * A_(i, j);
-    cn2[j] = sacc;
   }
   int rank = 0;
   double maxpiv = 0.;
@@ -1045,7 +1039,6 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
       double sacc = 0.;
       for (int i = k; i < n; i++)
         sacc += A_(i, j) * A_(i, j);
-      cn2[j] = sacc;
       if (sacc > best2) {
         best2 = sacc;
         piv = j;

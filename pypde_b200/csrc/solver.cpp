@@ -228,8 +228,58 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
           "cuFuncSetAttribute(k_dg smem)");
 }
 
+void Solver::finish_slot(SnapSlot &s) {
+  if (!s.dst)
+    return;
+  check(driver().EventSynchronize(s.done), "cuEventSynchronize(snapshot)");
+  memcpy(s.dst, s.pinned, (size_t)ncell_ * cfg_.V * sizeof(double));
+  s.dst = nullptr;
+}
+
+void Solver::snapshot_async(double *host_row) {
+  ensure_context();
+  const DriverApi &d = driver();
+  const size_t bytes = (size_t)ncell_ * cfg_.V * sizeof(double);
+  if (!copy_stream_)
+    check(d.StreamCreate(&copy_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate(copy)");
+  SnapSlot &s = snap_[snap_next_];
+  snap_next_ ^= 1;
+  finish_slot(s); // the slot's previous snapshot must have landed in its row
+  if (!s.pinned) {
+    s.dev.alloc(bytes);
+    check(d.MemAllocHost((void **)&s.pinned, bytes), "cuMemAllocHost(snapshot)");
+    check(d.EventCreate(&s.ready, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    check(d.EventCreate(&s.done, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+  }
+  check(d.MemcpyDtoDAsync(s.dev.p, u_, bytes, stream_), "cuMemcpyDtoDAsync(snapshot)");
+  check(d.EventRecord(s.ready, stream_), "cuEventRecord");
+  check(d.StreamWaitEvent(copy_stream_, s.ready, 0), "cuStreamWaitEvent");
+  check(d.MemcpyDtoHAsync(s.pinned, s.dev.p, bytes, copy_stream_), "cuMemcpyDtoHAsync(snapshot)");
+  check(d.EventRecord(s.done, copy_stream_), "cuEventRecord");
+  s.dst = host_row;
+}
+
+void Solver::drain_snapshots() {
+  for (SnapSlot &s : snap_)
+    finish_slot(s);
+}
+
 Solver::~Solver() {
   const DriverApi &d = driver();
+  for (SnapSlot &s : snap_) {
+    if (s.dst && s.done)
+      d.EventSynchronize(s.done);
+    if (s.pinned)
+      d.MemFreeHost(s.pinned);
+    if (s.ready)
+      d.EventDestroy(s.ready);
+    if (s.done)
+      d.EventDestroy(s.done);
+  }
+  if (copy_stream_) {
+    d.StreamSynchronize(copy_stream_);
+    d.StreamDestroy(copy_stream_);
+  }
   if (stream_)
     d.StreamSynchronize(stream_);
   if (own_stream_ && stream_)

@@ -79,6 +79,12 @@ public:
   void snapshot_prev(); // uprev <- u (iterator.cpp:147)
   void get_prev(double *u_host);
   size_t read_stage(int which, double *out, size_t cap);
+  // Snapshot pipeline (the `ret` rows of iterator.cpp:136-139): the state is copied
+  // device-to-device on the compute stream, then device-to-pinned-host on a copy
+  // stream, overlapping the following steps; the pinned buffer is copied into the
+  // caller's (pageable) row when its slot is reused or at drain_snapshots().
+  void snapshot_async(double *host_row);
+  void drain_snapshots();
 
   // stand-alone reconstruction of an already padded array (api.cpp:32-48)
   static void weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V);
@@ -128,6 +134,16 @@ private:
       flx_[3], state_;
   CUdeviceptr u_ = 0;
   StepState *h_state_ = nullptr; // pinned
+  struct SnapSlot {
+    DeviceBuffer dev;
+    double *pinned = nullptr;
+    CUevent ready = nullptr, done = nullptr;
+    double *dst = nullptr; // pending destination row, or null
+  };
+  SnapSlot snap_[2];
+  int snap_next_ = 0;
+  CUstream copy_stream_ = nullptr;
+  void finish_slot(SnapSlot &s);
 };
 
 } // namespace pypde

@@ -100,6 +100,29 @@ def test_ret_row_semantics():
     assert all(np.abs(out[k]).max() == 0 for k in range(len(filled) - 1, 39))
 
 
+def test_snapshot_rows_match_stepwise_states():
+    """Every ret row written by the asynchronous snapshot pipeline equals the state
+    of a step-by-step run at the step where iterator.cpp:136-139 pushes it."""
+    c = cases.solver_cases()['euler2d_smooth_N2']
+    F, B, S, V = cuda_sources('euler', 2)
+    ndt = 5
+    out, _ = run_gpu(c, ndt=ndt)
+    sol = Solver(c['Q0'].shape, c['L'], F=F, boundaryTypes=c['bts'], order=c['order'])
+    sol.set_state(c['Q0'])
+    sol.begin(c['tf'])
+    t, push, rows = 0., 0, {}
+    while t < c['tf']:
+        t, dt, nan = sol.step()
+        if t >= (push + 1) / ndt * c['tf'] and push < ndt:
+            rows[push] = sol.get_state()
+            push += 1
+    rows[ndt - 1] = sol.get_state()
+    sol.close()
+    assert push >= 3
+    for k, u in rows.items():
+        assert np.array_equal(out[k], u), k
+
+
 # ------------------------------------------------------------------ stage-wise
 @pytest.mark.parametrize('system,shape,N,bts', [
     ('euler', (48, ), 2, ['transitive']), ('euler', (48, ), 3, ['periodic']),

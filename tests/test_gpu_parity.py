@@ -14,6 +14,8 @@ Tolerances (relative L-infinity, max|a-b|/max|b|):
     for non-stiff systems; the self-noise (stored with the golden fixtures) exceeds
     it on shock data and with viscous fluxes (conftest.parity_tolerance).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -238,6 +240,36 @@ def test_reference_style_functions_through_pde_solver(golden, name, F):
     out = pypde_b200.pde_solver(Q0, c['tf'], c['L'], F=F, boundaryTypes=c['bts'],
                                 order=c['order'], ndt=1, stiff=False)
     assert rel_linf(out[0], golden['solver'][name]) < parity_tolerance(golden['solver'], name)
+
+
+# --------------------------------- BASELINE config 2 against the reference itself
+def test_config2_against_reference_library_128():
+    """2-D Euler explosion, order 3, Rusanov (BASELINE configs[1]) on 128^2 for 12
+    steps, GPU vs the UNMODIFIED reference (oracle/_ref travels with the repo),
+    next to the reference's own +-1 ulp self-noise measured in the same test."""
+    from oracle import reference as R
+    if not R.available('libpypde_ref.so'):
+        pytest.skip('oracle/_ref not built')
+    n = 128
+    Q0 = cases.euler_explosion((n, n))
+    tf = 9 * 0.2 * 0.9 / (2 * np.sqrt(1.4) * n)     # 6 start-up steps + a few full ones
+    cF, _, _ = R.system_callbacks('euler', 2)
+    threads = max(1, (os.cpu_count() or 2) - 1)
+
+    def ref(Q):
+        return R.pde_solver(Q, tf, [1., 1.], F=cF, order=3, ndt=1, stiff=False,
+                            nThreads=threads)[0]
+
+    a = ref(Q0)
+    rng = np.random.default_rng(1)
+    Qp = np.where(rng.random(Q0.shape) < 0.5, np.nextafter(Q0, np.inf), np.nextafter(Q0, -np.inf))
+    noise = rel_linf(ref(Qp), a)
+    F, B, S, V = cuda_sources('euler', 2)
+    out = pypde_b200.pde_solver(Q0.copy(), tf, [1., 1.], F=F, order=3, ndt=1, stiff=False)[0]
+    err = rel_linf(out, a)
+    print('config 2 at 128^2: GPU vs reference %.2e, reference self-noise %.2e' % (err, noise))
+    assert np.abs(a - Q0).max() > 1e-2
+    assert err < max(1e-10, 10 * noise)
 
 
 # ------------------------------------------------- size-independent properties

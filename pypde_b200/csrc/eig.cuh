@@ -405,10 +405,45 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     rho = fabs(mu);
     return true;
   }
-  // Faddeev-LeVerrier: M_1 = B, c_{n-1} = -tr M_1 (= 0); M_k = B (M_{k-1} + c_{n-k+1} I),
-  // c_{n-k} = -tr(M_k)/k
   double c[n];
   c[n - 1] = 0.;
+  if (n == 3) {
+    // p(y) = y^3 + c1 y + c0: c1 = sum of principal 2 x 2 minors, c0 = -det B
+    const double m01 = fma(B[0], B[4], -(B[1] * B[3]));
+    const double m02 = fma(B[0], B[8], -(B[2] * B[6]));
+    const double m12 = fma(B[4], B[8], -(B[5] * B[7]));
+    c[1] = m01 + m02 + m12;
+    const double d0 = fma(B[4], B[8], -(B[5] * B[7]));
+    const double d1 = fma(B[3], B[8], -(B[5] * B[6]));
+    const double d2 = fma(B[3], B[7], -(B[4] * B[6]));
+    c[0] = -(fma(B[0], d0, fma(-B[1], d1, B[2] * d2)));
+  } else if (n == 4) {
+    // p(y) = y^4 + c2 y^2 + c1 y + c0 from the principal minors of B (about half the
+    // work of the general recurrence below):
+    //   c2 = sum of principal 2 x 2 minors, c1 = -sum of principal 3 x 3 minors, c0 = det B
+#define B_(i, j) B[(i) * 4 + (j)]
+#define MIN2(i, j) fma(B_(i, i), B_(j, j), -(B_(i, j) * B_(j, i)))
+    c[2] = ((MIN2(0, 1) + MIN2(0, 2)) + (MIN2(0, 3) + MIN2(1, 2))) + (MIN2(1, 3) + MIN2(2, 3));
+#define DET3(i, j, k)                                                                             \
+  fma(B_(i, i), fma(B_(j, j), B_(k, k), -(B_(j, k) * B_(k, j))),                                  \
+      fma(-B_(i, j), fma(B_(j, i), B_(k, k), -(B_(j, k) * B_(k, i))),                             \
+          B_(i, k) * fma(B_(j, i), B_(k, j), -(B_(j, j) * B_(k, i)))))
+    c[1] = -((DET3(0, 1, 2) + DET3(0, 1, 3)) + (DET3(0, 2, 3) + DET3(1, 2, 3)));
+    // det by complementary 2 x 2 minors of rows (0,1) and (2,3)
+#define M01(p, q) fma(B_(0, p), B_(1, q), -(B_(0, q) * B_(1, p)))
+#define M23(p, q) fma(B_(2, p), B_(3, q), -(B_(2, q) * B_(3, p)))
+    c[0] = fma(M01(0, 1), M23(2, 3),
+               fma(-M01(0, 2), M23(1, 3),
+                   fma(M01(0, 3), M23(1, 2),
+                       fma(M01(1, 2), M23(0, 3), fma(-M01(1, 3), M23(0, 2), M01(2, 3) * M23(0, 1))))));
+#undef M01
+#undef M23
+#undef DET3
+#undef MIN2
+#undef B_
+  } else {
+  // Faddeev-LeVerrier: M_1 = B, c_{n-1} = -tr M_1 (= 0); M_k = B (M_{k-1} + c_{n-k+1} I),
+  // c_{n-k} = -tr(M_k)/k
   double M[n * n];
 #pragma unroll
   for (int i = 0; i < n * n; i++)
@@ -450,6 +485,7 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
           tr = fma(B[i * n + l], M[l * n + i], tr);
       c[0] = -tr * (1. / n);
     }
+  }
   }
 
   // every root satisfies |y| <= ||B||_inf; for a real spectrum with zero mean also

@@ -243,6 +243,7 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 // shifted characteristic polynomial.
 struct EigGuess {
   double yp, ym; // largest / smallest real root of the previous solve (shifted)
+  double rel;    // relative change of the roots between the last two solves
   int valid;
 };
 
@@ -330,10 +331,11 @@ template <int m> struct PolyRoots {
   // Largest real root of x^m + c[m-1] x^(m-1) + .. + c[0].  Start: `guess` (> 0
   // means given) nudged right by 1e-3 if certified to be right of every real root,
   // else x_cold, which the caller guarantees to be.  false = fall back to QR.
-  static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root) {
+  static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root,
+                               double nudge = 1e-3) {
     double x = x_cold;
     if (guess > 0.) {
-      const double xg = guess * (1. + 1e-3);
+      const double xg = guess * (1. + nudge);
       if (xg <= x_cold && right_of_all_roots(c, xg))
         x = xg;
     }
@@ -494,9 +496,14 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   // certificate inside rightmost(); x0 is the unconditional one.
   const double x0 = R * (1. + 1e-12);
   double gp = -1., gm = -1.;
+  // how far to the right of the guess the iteration starts: four times the last
+  // observed relative change of the roots (a sequence of nearby states), within
+  // [1e-7, 1e-3]; the Budan-Fourier certificate decides whether that was enough
+  double nudge = 1e-3;
   if (guess && guess->valid) {
     gp = guess->yp;
     gm = -guess->ym;
+    nudge = fmin(1e-3, fmax(1e-7, 4. * guess->rel));
   } else if (c[n - 2] < 0.) {
     gp = gm = sqrt(-2. * c[n - 2] * ((n - 1.) / n));
   }
@@ -511,9 +518,9 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   if (!PolyRoots<n>::outer_pair(c, cm, x0, gp, gm, yp, ym))
     return false;
 #else
-  if (!PolyRoots<n>::rightmost(c, x0, gp, yp))
+  if (!PolyRoots<n>::rightmost(c, x0, gp, yp, nudge))
     return false;
-  if (!PolyRoots<n>::rightmost(cm, x0, gm, ym))
+  if (!PolyRoots<n>::rightmost(cm, x0, gm, ym, nudge))
     return false;
 #endif
   ym = -ym;
@@ -565,6 +572,9 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     }
     rho = best;
     if (guess) {
+      guess->rel = guess->valid ? fmax(fabs(yp - guess->yp), fabs(ym - guess->ym)) /
+                                      fmax(fabs(yp), fabs(ym))
+                                : 2.5e-4;
       guess->yp = yp;
       guess->ym = ym;
       guess->valid = 1;
@@ -602,6 +612,9 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   }
   rho = best;
   if (guess) {
+    guess->rel = guess->valid ? fmax(fabs(yp - guess->yp), fabs(ym - guess->ym)) /
+                                    fmax(fabs(yp), fabs(ym))
+                              : 2.5e-4;
     guess->yp = yp;
     guess->ym = ym;
     guess->valid = 1;

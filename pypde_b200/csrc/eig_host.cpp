@@ -22,7 +22,7 @@ extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_on
       std::vector<double> w(a);                                                                   \
       for (size_t i = 0; i < w.size(); i++)                                                       \
         w[i] *= 1. + 1e-5 * ((int)(i % 7) - 3);                                                   \
-      EigGuess g{0., 0., 0};                                                                      \
+      EigGuess g{0., 0., 0., 0};                                                                      \
       spectral_radius<N>(w.data(), nullptr, &g);                                                  \
       r = spectral_radius<N>(a.data(), &pth, &g);                                                 \
     } else {                                                                                      \

@@ -562,7 +562,7 @@ void Solver::step_async() {
     launch(mod_->k_dg, (unsigned)nblocks, block, smem, args, "k_dg");
   }
   if (cfg_.useF && cfg_.flux == 0) {
-    long total = ncellw_ * 2 * nd * ipow(N, nd - 1);
+    long total = ncellw_ * 2 * nd;
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
     launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, 0, args,
            "k_wavespeeds");

@@ -54,7 +54,7 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
     }
   for (const char *e : {"PYPDE_B200_EXTRA_DEFINES", "PYPDE_B200_FMA", "PYPDE_B200_EXACT_B",
                         "PYPDE_B200_EIG_QR_ONLY", "PYPDE_B200_WS_BLOCK", "PYPDE_B200_WS_MINBLOCKS",
-                        "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB"}) {
+                        "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES"}) {
     const char *v = getenv(e);
     k += v ? v : "-";
     k += '|';

@@ -93,6 +93,8 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     get(k_wavespeeds, "k_wavespeeds");
   if (cfg.stiff)
     get(k_dg_stiff, "k_dg_stiff");
+  if (cfg.useF && cfg.flux == 0)
+    get(k_faces_fused, "k_faces_fused");
 }
 
 Module::~Module() {
@@ -114,6 +116,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   if (cfg_.flux < 0 || cfg_.flux > 2)
     throw std::runtime_error("pypde_b200: FLUX must be 0 (rusanov), 1 (roe) or 2 (osher)");
   choose_block_shapes(cfg_);
+  if (const char *e = getenv("PYPDE_B200_FUSED_FACES"))
+    fused_faces_ = *e != '0';
   ensure_context();
   const DriverApi &d = driver();
   CUdevice dev;
@@ -561,13 +565,21 @@ void Solver::step_async() {
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
     launch(mod_->k_dg, (unsigned)nblocks, block, smem, args, "k_dg");
   }
-  if (cfg_.useF && cfg_.flux == 0) {
+  // Rusanov: one fused pass per direction (k_faces_fused); PYPDE_B200_FUSED_FACES=0 keeps
+  // the two-kernel path (k_wavespeeds + k_faces), which Roe / Osher / no-F always use
+  if (cfg_.useF && cfg_.flux == 0 && fused_faces_) {
+    for (int dd = 0; dd < nd; dd++) {
+      void *args[] = {&traces_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
+      launch(mod_->k_faces_fused, grid_for(nfaces_[dd], cfg_.ws_block), cfg_.ws_block, 0, args,
+             "k_faces_fused");
+    }
+  } else if (cfg_.useF && cfg_.flux == 0) {
     long total = ncellw_ * 2 * nd;
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
     launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, 0, args,
            "k_wavespeeds");
   }
-  if (cfg_.useF || cfg_.useB) {
+  if ((cfg_.useF || cfg_.useB) && !(cfg_.useF && cfg_.flux == 0 && fused_faces_)) {
     const int NP = N * ipow(N, nd - 1);
     const int FLXW = cfg_.useB ? 2 : 1;
     for (int dd = 0; dd < nd; dd++) {

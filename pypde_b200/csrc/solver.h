@@ -59,7 +59,7 @@ public:
   CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
-             k_wavespeeds = nullptr, k_dg_stiff = nullptr;
+             k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr;
 };
 
 class Solver {
@@ -128,6 +128,7 @@ private:
   bool own_stream_ = false;
 
   DeviceBuffer stiff_work_;
+  bool fused_faces_ = true;
   int stiff_wpb_ = 4;
   long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,

@@ -87,7 +87,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '20'],
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -257,18 +257,19 @@ def main():
     sol.set_stream(stream.cuda_stream)
     sol.bind_tensor(u_dev)
     sol.begin(1e9)
+    # clocks are sampled from the warm-up through the timed region to the per-kernel
+    # pass (the GPU is under the same load throughout)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(W):
         sol.step_async()
     barrier()
     l0 = sol.launches
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(K):
         sol.step_async()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     launches = sol.launches - l0
     t_end, dt_last, nan = sol.sync()
@@ -283,11 +284,12 @@ def main():
 
     # ---- per-kernel device times (CUDA events on the launching stream), separate pass
     sol.set_profiling(True)
-    P = 3
+    P = 5
     for _ in range(P):
         sol.step_async()
     kt = sol.kernel_times()
     sol.set_profiling(False)
+    clocks = sampler.stop() if sampler else None
     fp64_peak = sol.fp64_peak_tflops()
     hbm_peak, peak_src = measured_peaks()
     kb, b_alg, f_alg, f_faces = algorithmic_model(n)

@@ -429,8 +429,10 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
 
       if (t >= double(pushCount + 1) / double(ndt) * tf && pushCount < ndt) {
         // asynchronous: D2D on the compute stream, D2H on a copy stream, overlapping
-        // the next steps
-        solver.snapshot_async(_ret + (size_t)pushCount * n);
+        // the next steps.  Row ndt-1 always receives the final state
+        // below (iterator.cpp:150), so a push into it need not be copied.
+        if (pushCount < ndt - 1)
+          solver.snapshot_async(_ret + (size_t)pushCount * n);
         pushCount += 1;
       }
       if (nan_found || std::isnan(t)) {
@@ -450,7 +452,7 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     // iterator.cpp:150 and the in-place update of _u (api.cpp:18, iterator.cpp:129)
     solver.get_state(_u);
     if (ndt >= 1)
-      memcpy(_ret + (size_t)(ndt - 1) * n, _u, n * sizeof(double));
+      solver.get_state(_ret + (size_t)(ndt - 1) * n);
   } catch (const std::exception &e) {
     set_error(e.what());
   } catch (...) {

@@ -22,6 +22,8 @@ def ncu_instr(rep, kernel):
     cur, hdr, res, want_hdr = None, None, [], False
     for r in rows:
         if len(r) >= 2 and r[0] == 'Kernel Name':
+            if res:          # only the first captured launch of this kernel
+                break
             cur, want_hdr = r[1], True
             continue
         if cur != kernel:

@@ -26,6 +26,9 @@ using std::sqrt;
 #ifndef PDE_EIG_PAIR
 #define PDE_EIG_PAIR 0 // 1: iterate the two outer roots in one loop (two dependency chains)
 #endif
+#ifndef PDE_EIG_HALLEY
+#define PDE_EIG_HALLEY 1 // 1: warm-started root searches take a Halley step from the certificate
+#endif
 #ifndef PDE_EIG_QR_ONLY
 #define PDE_EIG_QR_ONLY 0 // 1: always use the general QR iteration for spectral radii
 #endif
@@ -334,13 +337,56 @@ template <int m> struct PolyRoots {
   static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root,
                                double nudge = 1e-3) {
     double x = x_cold;
+    bool newton = false;
+    int state = 0;
+#if PDE_EIG_HALLEY
+    // Warm start.  The Taylor coefficients of p at the nudged guess serve twice: all
+    // positive certifies that no real root lies to the right of it (Budan-Fourier),
+    // and t0, t1, t2 = p, p', p''/2 give the first step for free — Halley's
+    //   a = p p' / (p'^2 - p p''/2)
+    // (cubic, one division, no square root; it lies between the Newton and the
+    // Laguerre step, so it is monotone in the same regime).  A step below 4e-7 |x|
+    // leaves an error ~ (step / |x|)^3 times the root's conditioning, i.e. rounding
+    // level for every root the caller goes on to certify: no polishing pass.
+    if (guess > 0.) {
+      const double xg = guess * (1. + nudge);
+      if (xg <= x_cold) {
+        double t[m + 1];
+#pragma unroll
+        for (int k = 0; k < m; k++)
+          t[k] = c[k];
+        t[m] = 1.;
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < m; i++) {
+#pragma unroll
+          for (int k = m - 1; k >= i; k--)
+            t[k] = fma(xg, t[k + 1], t[k]);
+          ok = ok && (t[i] > 0.);
+        }
+        if (ok) {
+          x = xg;
+          const double den = fma(t[1], t[1], -(t[0] * t[2]));
+          const double a = (t[0] * t[1]) / den;
+          if (den > 0. && a >= 0. && a <= 1e300) {
+            x = xg - a;
+            const double ax = fabs(x);
+            if (a <= 4e-7 * ax) {
+              root = x;
+              return true;
+            }
+            newton = a <= 0.02 * ax;
+          }
+        }
+      }
+    }
+#else
     if (guess > 0.) {
       const double xg = guess * (1. + nudge);
       if (xg <= x_cold && right_of_all_roots(c, xg))
         x = xg;
     }
-    bool newton = false;
-    int state = 0;
+#endif
     for (int it = 0; it < 30 && state == 0; it++)
       step(c, x, newton, state, root);
     return state == 1;

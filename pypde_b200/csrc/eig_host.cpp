@@ -14,16 +14,21 @@ extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_on
   case N:                                                                                         \
     if (qr_only == 2) {                                                                           \
       r = spectral_radius_qr<N>(a.data());                                                        \
-    } else if (qr_only) {                                                                         \
+    } else if (qr_only == 1) {                                                                       \
       if (N > 2)                                                                                  \
         balance<N>(a.data());                                                                     \
       r = spectral_radius_qr<N>(a.data());                                                        \
-    } else if (qr_only == 3) { /* warm start: solve a perturbed copy first, then this one */      \
-      std::vector<double> w(a);                                                                   \
-      for (size_t i = 0; i < w.size(); i++)                                                       \
-        w[i] *= 1. + 1e-5 * ((int)(i % 7) - 3);                                                   \
-      EigGuess g{0., 0., 0., 0};                                                                      \
-      spectral_radius<N>(w.data(), nullptr, &g);                                                  \
+    } else if (qr_only == 3 || qr_only == 4) {                                                    \
+      /* warm start: solve perturbed copies first (mode 3: one, 1e-5 away; mode 4: a second     \
+         two 1e-9 away, so that the last solve starts a relative 1e-7 from its roots) */        \
+      EigGuess g{0., 0., 0., 0};                                                                  \
+      for (int rep = 0; rep < (qr_only == 3 ? 1 : 3); rep++) {                                    \
+        std::vector<double> w(a);                                                                 \
+        const double eps = rep == 0 ? 1e-5 : rep * 1e-9;                                          \
+        for (size_t i = 0; i < w.size(); i++)                                                     \
+          w[i] *= 1. + eps * ((int)(i % 7) - 3);                                                  \
+        spectral_radius<N>(w.data(), nullptr, &g);                                                \
+      }                                                                                           \
       r = spectral_radius<N>(a.data(), &pth, &g);                                                 \
     } else {                                                                                      \
       r = spectral_radius<N>(a.data(), &pth);                                                     \
@@ -36,7 +41,7 @@ extern "C" int pypde_b200_host_spectral_radius(const double *A, int n, int qr_on
 #undef CASE
   *rho = r;
   if (path)
-    *path = qr_only ? 0 : pth;
+    *path = (qr_only == 1 || qr_only == 2) ? 0 : pth;
   return 0;
 }
 

@@ -17,7 +17,7 @@ struct KernelConfig {
   int dg_cpb = 1;    // cells per block in k_dg
   int faces_fpb = 1; // faces per block in k_faces
   int stiff_wpb = 4; // warps (cells) per block in k_dg_stiff
-  int ws_block = 512, ws_minblocks = 1; // k_wavespeeds launch bounds (512 measured best)
+  int ws_block = 256, ws_minblocks = 2; // wave-speed / fused-face launch bounds (measured best)
 };
 
 // Chooses the block shapes for a configuration (threads <= 256 where possible,

@@ -224,6 +224,20 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
                                (int)(stiff_wpb_ * smem_warp)),
             "cuFuncSetAttribute(k_dg_stiff smem)");
   }
+  // the predictor kernels keep their working set in shared memory and run many small
+  // blocks per SM: ask for the largest shared-memory carve-out so that residency is
+  // bounded by registers, not by the driver's default L1 / shared split
+  {
+    int carve = 100; // percent of the maximum (CU_SHAREDMEM_CARVEOUT_MAX_SHARED)
+    if (const char *e = getenv("PYPDE_B200_DG_CARVEOUT"))
+      carve = atoi(e);
+    if (carve >= 0) {
+      d.FuncSetAttribute(mod_->k_dg, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, carve);
+      if (cfg_.stiff)
+        d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT,
+                           carve);
+    }
+  }
   // dynamic shared memory opt-in
   const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;
   if (dg_smem > 48 * 1024)

@@ -148,18 +148,25 @@ def test_edge_cases():
 
 
 def test_warm_start_gives_the_cold_result():
-    """mode 3 of the host entry solves a perturbed copy first and warm-starts the
-    real solve from its outer roots (as k_wavespeeds does across time nodes)."""
+    """modes 3 / 4 of the host entry solve one / two perturbed copies first and warm-start
+    the real solve from their outer roots (as k_faces_fused does along a face's quadrature
+    points): mode 3 starts ~1e-3 to the right of the roots (Halley step, then the generic
+    iteration), mode 4 ~1e-7 (the Halley step alone ends the search)."""
     rng = np.random.default_rng(11)
     for n in (3, 4, 5):
         for kind in ('real', 'euler'):
+            fast = 0
             for _ in range(300):
                 D, true = spectrum_case(n, kind, rng)
                 A = similar(D, rng)
                 cold, _ = rho(A)
-                warm, _ = rho(A, 3)
-                assert abs(warm - cold) <= 1e-13 * cold
-                assert abs(warm - true) / true < 2e-13
+                for mode in (3, 4):
+                    warm, path = rho(A, mode)
+                    fast += path
+                    assert abs(warm - cold) <= 1e-13 * cold, (n, kind, mode)
+                    assert abs(warm - true) / true < 2e-13
+            if kind == 'euler':
+                assert fast > 500
 
 
 def abs_apply(A, x):

@@ -62,6 +62,7 @@ def algorithmic_model(n):
         'k_weno_sweep': None,  # two launches with different sizes, summed below
         'k_cfl': cw * Nd * V * D,
         'k_dg': cw * (Nd * V + 2 * NDIM * NP * V) * D,
+        'k_dg_n': cw * (Nd * V + 2 * NDIM * NP * V) * D,             # w in, face traces out
         'k_faces_fused': n * (n + 1) * (2 * NP * V + V) * D,         # per direction: traces in, flux out
         'k_wavespeeds': cw * 2 * NDIM * NP * (V + 1) * D,            # traces in, lambda out
         'k_faces': n * (n + 1) * (2 * NP * (V + 1) + V) * D,         # per direction
@@ -78,8 +79,11 @@ def algorithmic_model(n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+    """nvidia-smi clocks / throttle reasons during the timed region.  The sampler is
+    started early (nvidia-smi takes a second to come up) and runs through the whole
+    bench; stop(t0, t1) keeps the samples whose time stamp lies in the wall-clock
+    window [t0, t1] of the load (warm-up, timed steps, per-kernel pass)."""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
@@ -87,12 +91,13 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
         if self.p is None:
             return out
@@ -104,22 +109,29 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, reasons, mx = [], set(), None
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        parsed = []
         for r in rows:
             try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
+                ts = datetime.datetime.strptime(r[0].strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rec = (ts, float(r[1]), float(r[2]), float(r[3]),
+                       [nme for k, nme in enumerate(names)
+                        if len(r) > 4 + k and r[4 + k].strip().lower() == 'active'])
             except (ValueError, IndexError):
                 continue
-            for k, nme in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].strip().lower() == 'active':
-                    reasons.add(nme)
-        if sm:
-            out['sm_mhz'] = float(np.median(sm))
-            out['sm_max_mhz'] = mx
-            out['samples'] = len(sm)
-        out['reasons'] = sorted(reasons)
+            parsed.append(rec)
+        inside = [r for r in parsed if t0 is None or (t0 - 0.02 <= r[0] <= t1 + 0.02)]
+        if not inside and parsed and t0 is not None:
+            # none landed inside the window: the sample nearest to it
+            inside = [min(parsed, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))]
+            out['note'] = 'no sample inside the load window; nearest sample reported'
+        if inside:
+            out['sm_mhz'] = float(np.median([r[1] for r in inside]))
+            out['sm_max_mhz'] = inside[-1][2]
+            out['power_w_max'] = max(r[3] for r in inside)
+            out['samples'] = len(inside)
+            out['window_s'] = None if t0 is None else round(t1 - t0, 3)
+            out['reasons'] = sorted({x for r in inside for x in r[4]})
         return out
 
 
@@ -237,6 +249,7 @@ def main():
         comm_init_from_torch()
 
     os.environ['PYPDE_B200_QUIET'] = '1'
+    sampler = ClockSampler(local) if rank == 0 else None
     n = args.size
     K, W = args.steps, args.warmup
     F, B, S, v = cuda_sources('euler', 2)
@@ -259,7 +272,8 @@ def main():
     sol.begin(1e9)
     # clocks are sampled from the warm-up through the timed region to the per-kernel
     # pass (the GPU is under the same load throughout)
-    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t_load0 = time.time()
     for _ in range(W):
         sol.step_async()
     barrier()
@@ -289,7 +303,8 @@ def main():
         sol.step_async()
     kt = sol.kernel_times()
     sol.set_profiling(False)
-    clocks = sampler.stop() if sampler else None
+    t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1) if sampler else None
     fp64_peak = sol.fp64_peak_tflops()
     hbm_peak, peak_src = measured_peaks()
     kb, b_alg, f_alg, f_faces = algorithmic_model(n)

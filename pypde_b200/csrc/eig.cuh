@@ -23,12 +23,10 @@ using std::sqrt;
 #endif
 
 #define DBL_EPS 2.2204460492503131e-16
-#ifndef PDE_EIG_PAIR
-#define PDE_EIG_PAIR 0 // 1: iterate the two outer roots in one loop (two dependency chains)
-#endif
-#ifndef PDE_EIG_HALLEY
-#define PDE_EIG_HALLEY 1 // 1: warm-started root searches take a Halley step from the certificate
-#endif
+
+// max of two non-NaN values as one compare + select (fmax's NaN semantics cost extra
+// instructions in the hot path)
+EIG_FN double sel_max(double a, double b) { return a > b ? a : b; }
 #ifndef PDE_EIG_QR_ONLY
 #define PDE_EIG_QR_ONLY 0 // 1: always use the general QR iteration for spectral radii
 #endif
@@ -246,30 +244,11 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 // shifted characteristic polynomial.
 struct EigGuess {
   double yp, ym; // largest / smallest real root of the previous solve (shifted)
-  double rel;    // relative change of the roots between the last two solves
+  double dy;     // change of the outer roots between the last two solves
   int valid;
 };
 
 template <int m> struct PolyRoots {
-  // Budan-Fourier certificate: every Taylor coefficient of p at x positive means
-  // no real root lies to the right of x.
-  static EIG_FN bool right_of_all_roots(const double *c, double x) {
-    double t[m + 1];
-#pragma unroll
-    for (int k = 0; k < m; k++)
-      t[k] = c[k];
-    t[m] = 1.;
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < m; i++) {
-#pragma unroll
-      for (int k = m - 1; k >= i; k--)
-        t[k] = fma(x, t[k + 1], t[k]);
-      ok = ok && (t[i] > 0.);
-    }
-    return ok;
-  }
-
   // One monotone step towards the largest real root from a point to its right:
   // Laguerre's iteration in the one-division form
   //   a = m p / (p' + sqrt((m-1)((m-1) p'^2 - m p p'')))
@@ -331,93 +310,59 @@ template <int m> struct PolyRoots {
     newton = a <= 0.02 * ax;
   }
 
-  // Largest real root of x^m + c[m-1] x^(m-1) + .. + c[0].  Start: `guess` (> 0
-  // means given) nudged right by 1e-3 if certified to be right of every real root,
-  // else x_cold, which the caller guarantees to be.  false = fall back to QR.
-  static EIG_FN bool rightmost(const double *c, double x_cold, double guess, double &root,
-                               double nudge = 1e-3) {
-    double x = x_cold;
-    bool newton = false;
-    int state = 0;
-#if PDE_EIG_HALLEY
-    // Warm start.  The Taylor coefficients of p at the nudged guess serve twice: all
-    // positive certifies that no real root lies to the right of it (Budan-Fourier),
-    // and t0, t1, t2 = p, p', p''/2 give the first step for free — Halley's
-    //   a = p p' / (p'^2 - p p''/2)
-    // (cubic, one division, no square root; it lies between the Newton and the
-    // Laguerre step, so it is monotone in the same regime).  A step below 4e-7 |x|
-    // leaves an error ~ (step / |x|)^3 times the root's conditioning, i.e. rounding
-    // level for every root the caller goes on to certify: no polishing pass.
-    if (guess > 0.) {
-      const double xg = guess * (1. + nudge);
-      if (xg <= x_cold) {
-        double t[m + 1];
+  // Largest real root of x^m + c[m-1] x^(m-1) + .. + c[0] from a warm start xg (the
+  // previous solve's root moved right by the caller's margin).  The Taylor
+  // coefficients of p at xg serve twice: all positive certifies that no real root
+  // lies to the right of xg (Budan-Fourier), and t0, t1, t2 = p, p', p''/2 give the
+  // first step for free — Halley's
+  //   a = p p' / (p'^2 - p p''/2)
+  // (cubic, one division, no square root; it lies between the Newton and the
+  // Laguerre step, so it is monotone in the same regime).  A step below 4e-7 |x|
+  // leaves an error ~ (step / |x|)^3 times the root's conditioning, i.e. rounding
+  // level for every root the caller goes on to certify: no polishing pass.
+  // Returns 1: root found; 0: certified, iterate() continues from x; -1: xg is not
+  // certified (or not given), the caller must start from a bound on the spectrum.
+  static EIG_FN int start(const double *c, double xg, double &x, bool &newton, double &root) {
+    if (!(xg > 0.))
+      return -1;
+    double t[m + 1];
 #pragma unroll
-        for (int k = 0; k < m; k++)
-          t[k] = c[k];
-        t[m] = 1.;
-        bool ok = true;
+    for (int k = 0; k < m; k++)
+      t[k] = c[k];
+    t[m] = 1.;
+    bool ok = true;
 #pragma unroll
-        for (int i = 0; i < m; i++) {
+    for (int i = 0; i < m; i++) {
 #pragma unroll
-          for (int k = m - 1; k >= i; k--)
-            t[k] = fma(xg, t[k + 1], t[k]);
-          ok = ok && (t[i] > 0.);
-        }
-        if (ok) {
-          x = xg;
-          const double den = fma(t[1], t[1], -(t[0] * t[2]));
-          const double a = (t[0] * t[1]) / den;
-          if (den > 0. && a >= 0. && a <= 1e300) {
-            x = xg - a;
-            const double ax = fabs(x);
-            if (a <= 4e-7 * ax) {
-              root = x;
-              return true;
-            }
-            newton = a <= 0.02 * ax;
-          }
-        }
+      for (int k = m - 1; k >= i; k--)
+        t[k] = fma(xg, t[k + 1], t[k]);
+      ok = ok && (t[i] > 0.);
+    }
+    if (!ok)
+      return -1;
+    x = xg;
+    newton = false;
+    // (t0, t1 > 0 here; den <= 0, an overflow or a NaN leave the step to iterate())
+    const double den = fma(t[1], t[1], -(t[0] * t[2]));
+    const double a = (t[0] * t[1]) * (1. / den);
+    if (den > 0. && a <= 1e300) {
+      x = xg - a;
+      const double ax = fabs(x);
+      if (a <= 4e-7 * ax) {
+        root = x;
+        return 1;
       }
+      newton = a <= 0.02 * ax;
     }
-#else
-    if (guess > 0.) {
-      const double xg = guess * (1. + nudge);
-      if (xg <= x_cold && right_of_all_roots(c, xg))
-        x = xg;
-    }
-#endif
+    return 0;
+  }
+
+  // The monotone iteration from x, right of the largest real root.  false = fall back to QR.
+  static EIG_FN bool iterate(const double *c, double x, bool newton, double &root) {
+    int state = 0;
     for (int it = 0; it < 30 && state == 0; it++)
       step(c, x, newton, state, root);
     return state == 1;
-  }
-
-  // Largest root of c and of cm at once: the two iterations are independent, and
-  // running them in one loop gives the FP64 pipe two dependency chains to overlap.
-  static EIG_FN bool outer_pair(const double *c, const double *cm, double x_cold, double gp,
-                                double gm, double &rp, double &rm) {
-    double xp = x_cold, xm = x_cold;
-    if (gp > 0.) {
-      const double xg = gp * (1. + 1e-3);
-      if (xg <= x_cold && right_of_all_roots(c, xg))
-        xp = xg;
-    }
-    if (gm > 0.) {
-      const double xg = gm * (1. + 1e-3);
-      if (xg <= x_cold && right_of_all_roots(cm, xg))
-        xm = xg;
-    }
-    bool np = false, nm = false;
-    int sp = 0, sm = 0;
-    for (int it = 0; it < 30; it++) {
-      if (sp == 0)
-        step(c, xp, np, sp, rp);
-      if (sm == 0)
-        step(cm, xm, nm, sm, rm);
-      if ((sp != 0 && sm != 0) || sp < 0 || sm < 0)
-        break;
-    }
-    return sp == 1 && sm == 1;
   }
 };
 
@@ -436,23 +381,11 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     mu += A[i * n + i];
   mu *= (1. / n);
   double B[n * n];
-  double R = 0.;
 #pragma unroll
-  for (int i = 0; i < n; i++) {
-    double rs = 0.;
+  for (int i = 0; i < n; i++)
 #pragma unroll
-    for (int j = 0; j < n; j++) {
+    for (int j = 0; j < n; j++)
       B[i * n + j] = A[i * n + j] - (i == j ? mu : 0.);
-      rs += fabs(B[i * n + j]);
-    }
-    R = fmax(R, rs);
-  }
-  if (!(R <= 1e150)) // NaN or huge: leave it to the general routine
-    return false;
-  if (R == 0.) {
-    rho = fabs(mu);
-    return true;
-  }
   double c[n];
   c[n - 1] = 0.;
   if (n == 3) {
@@ -536,22 +469,21 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   }
   }
 
-  // every root satisfies |y| <= ||B||_inf; for a real spectrum with zero mean also
-  // |y| <= sqrt((n-1)/n sum y_i^2) = sqrt(-2 c_{n-2} (n-1)/n) (Laguerre-Samuelson),
-  // usually much tighter.  The tighter start is used only under the Budan-Fourier
-  // certificate inside rightmost(); x0 is the unconditional one.
-  const double x0 = R * (1. + 1e-12);
-  double gp = -1., gm = -1.;
-  // how far to the right of the guess the iteration starts: four times the last
-  // observed relative change of the roots (a sequence of nearby states), within
-  // [1e-7, 1e-3]; the Budan-Fourier certificate decides whether that was enough
-  double nudge = 1e-3;
+  // Starting points.  Warm: the previous solve's outer roots moved outwards by four
+  // times the last observed change of the roots (a sequence of nearby states), within
+  // [1e-7, 1e-3] relative; first solve of a sequence: the Laguerre-Samuelson bound
+  // sqrt((n-1)/n sum y_i^2) = sqrt(-2 c_{n-2} (n-1)/n) of a real zero-mean spectrum.
+  // Either is used only under the Budan-Fourier certificate inside from_guess();
+  // the unconditional start is ||B||_inf, which bounds every root and is computed
+  // only when a certificate fails.
+  double xgp = -1., xgm = -1.;
   if (guess && guess->valid) {
-    gp = guess->yp;
-    gm = -guess->ym;
-    nudge = fmin(1e-3, fmax(1e-7, 4. * guess->rel));
+    const double gp = guess->yp, gm = -guess->ym, d4 = 4. * guess->dy;
+    const double lp = 1e-7 * gp, hp = 1e-3 * gp, lm = 1e-7 * gm, hm = 1e-3 * gm;
+    xgp = gp + (d4 > hp ? hp : (d4 > lp ? d4 : lp)); // (plain selects: no NaN handling needed)
+    xgm = gm + (d4 > hm ? hm : (d4 > lm ? d4 : lm));
   } else if (c[n - 2] < 0.) {
-    gp = gm = sqrt(-2. * c[n - 2] * ((n - 1.) / n));
+    xgp = xgm = sqrt(-2. * c[n - 2] * ((n - 1.) / n)) * (1. + 1e-3);
   }
   // outermost real roots of the undeflated polynomial; the leftmost root of p is
   // minus the rightmost root of (-1)^n p(-y)
@@ -559,20 +491,49 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
 #pragma unroll
   for (int k = 0; k < n; k++)
     cm[k] = ((n - k) & 1) ? -c[k] : c[k];
-  double yp, ym;
-#if PDE_EIG_PAIR
-  if (!PolyRoots<n>::outer_pair(c, cm, x0, gp, gm, yp, ym))
+  double yp, ym, xp = 0., xm = 0.;
+  bool np = false, nm = false;
+  int sp = PolyRoots<n>::start(c, xgp, xp, np, yp);
+  int sm = PolyRoots<n>::start(cm, xgm, xm, nm, ym);
+  if (sp < 0 || sm < 0) {
+    double R = 0.;
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double rs = 0.;
+#pragma unroll
+      for (int j = 0; j < n; j++)
+        rs += fabs(B[i * n + j]);
+      R = fmax(R, rs);
+    }
+    if (!(R <= 1e150)) // NaN or huge: leave it to the general routine
+      return false;
+    if (R == 0.) {
+      rho = fabs(mu);
+      return true;
+    }
+    if (sp < 0) {
+      xp = R * (1. + 1e-12);
+      np = false;
+      sp = 0;
+    }
+    if (sm < 0) {
+      xm = R * (1. + 1e-12);
+      nm = false;
+      sm = 0;
+    }
+  }
+  if (sp == 0)
+    sp = PolyRoots<n>::iterate(c, xp, np, yp) ? 1 : 2;
+  if (sp == 1 && sm == 0)
+    sm = PolyRoots<n>::iterate(cm, xm, nm, ym) ? 1 : 2;
+  if (sp != 1 || sm != 1)
     return false;
-#else
-  if (!PolyRoots<n>::rightmost(c, x0, gp, yp, nudge))
-    return false;
-  if (!PolyRoots<n>::rightmost(cm, x0, gm, ym, nudge))
-    return false;
-#endif
   ym = -ym;
   // both searches ending on the same root means a single real root (n odd) or a
   // multiple one
-  const bool single = !(yp - ym > 1e-7 * R);
+  const double ayp = fabs(yp), aym = fabs(ym);
+  const double ymax = ayp > aym ? ayp : aym;
+  const bool single = !(yp - ym > 1e-7 * ymax);
   if (single && n != 3)
     return false;
 
@@ -618,9 +579,7 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     }
     rho = best;
     if (guess) {
-      guess->rel = guess->valid ? fmax(fabs(yp - guess->yp), fabs(ym - guess->ym)) /
-                                      fmax(fabs(yp), fabs(ym))
-                                : 2.5e-4;
+      guess->dy = guess->valid ? sel_max(fabs(yp - guess->yp), fabs(ym - guess->ym)) : 2.5e-4 * ymax;
       guess->yp = yp;
       guess->ym = ym;
       guess->valid = 1;
@@ -647,7 +606,7 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     if (!(fabs(mu) + fb <= 0.98 * best)) {
       double ce[3] = {e[0], e[1], e[2]};
       double yr;
-      if (!PolyRoots<3>::rightmost(ce, fmin(fb, x0) * (1. + 1e-12), -1., yr))
+      if (!PolyRoots<3>::iterate(ce, fb * (1. + 1e-12), false, yr))
         return false;
       const double g1 = ce[2] + yr;
       const double g0 = fma(g1, yr, ce[1]);
@@ -658,9 +617,7 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   }
   rho = best;
   if (guess) {
-    guess->rel = guess->valid ? fmax(fabs(yp - guess->yp), fabs(ym - guess->ym)) /
-                                    fmax(fabs(yp), fabs(ym))
-                              : 2.5e-4;
+    guess->dy = guess->valid ? sel_max(fabs(yp - guess->yp), fabs(ym - guess->ym)) : 2.5e-4 * ymax;
     guess->yp = yp;
     guess->ym = ym;
     guess->valid = 1;

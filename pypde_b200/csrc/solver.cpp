@@ -95,6 +95,9 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     get(k_dg_stiff, "k_dg_stiff");
   if (cfg.useF && cfg.flux == 0)
     get(k_faces_fused, "k_faces_fused");
+  // kernels.cuh: DGN_OK
+  if (!cfg.useB && !cfg.secondOrder && cfg.N >= 2 && ipow(cfg.N, cfg.ndim) <= 32)
+    get(k_dg_n, "k_dg_n");
 }
 
 Module::~Module() {
@@ -118,6 +121,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   choose_block_shapes(cfg_);
   if (const char *e = getenv("PYPDE_B200_FUSED_FACES"))
     fused_faces_ = *e != '0';
+  if (const char *e = getenv("PYPDE_B200_DG_NODE"))
+    node_dg_ = *e != '0';
   ensure_context();
   const DriverApi &d = driver();
   CUdevice dev;
@@ -569,6 +574,15 @@ void Solver::step_async() {
     const size_t smem = (size_t)stiff_wpb_ * (6 + nd) * N * Nd * V * sizeof(double);
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p, &stiff_work_.p};
     launch(mod_->k_dg_stiff, (unsigned)stiff_blocks_, 32 * stiff_wpb_, smem, args, "k_dg_stiff");
+  } else if (node_dg_ && mod_->k_dg_n) {
+    // one thread per spatial node, 32 / N^ndim cells per one-warp block
+    const int cpw = 32 / Nd;
+    long nblocks = (ncellw_ + cpw - 1) / cpw;
+    long cap = (long)sms_ * 32;
+    if (nblocks > cap)
+      nblocks = cap;
+    void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
+    launch(mod_->k_dg_n, (unsigned)nblocks, (unsigned)(cpw * Nd), 0, args, "k_dg_n");
   } else {
     const unsigned block = cfg_.dg_cpb * N * Nd;
     const size_t smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * sizeof(double);

@@ -59,7 +59,7 @@ public:
   CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
-             k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr;
+             k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr, k_dg_n = nullptr;
 };
 
 class Solver {
@@ -129,6 +129,7 @@ private:
 
   DeviceBuffer stiff_work_;
   bool fused_faces_ = true;
+  bool node_dg_ = true; // k_dg_n where it applies (PYPDE_B200_DG_NODE=0: always k_dg)
   int stiff_wpb_ = 4;
   long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,

@@ -97,6 +97,14 @@ int pypde_b200_tables(int N, double *nodes, double *wghts, double *derv, double 
 int pypde_b200_host_spectral_radius(const double *A, int n, int qr_only, double *rho,
                                     int *path);
 
+/* Same text, the two-matrix entry the fused face kernel uses (n = 3..5): the left and
+ * the right state's polynomials searched in lockstep, cold pass then warm pass.
+ * rho[2], ok[2]; ok[s] = 0 where the polynomial path deferred to the QR iteration.
+ * qr_only modes of the entry above: 1 balanced QR, 2 unbalanced QR, 3 / 4 warm starts
+ * from one / three perturbed copies. */
+int pypde_b200_host_spectral_radius_pair(const double *A0, const double *A1, int n, double *rho,
+                                         int *ok);
+
 /* Same, for the Osher/Roe dissipation y = |A| x = Re(R |Lambda| R^-1 x). */
 int pypde_b200_host_abs_matrix_apply(const double *A, int n, const double *x, double *y);
 

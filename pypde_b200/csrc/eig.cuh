@@ -19,6 +19,7 @@ using std::fma;
 using std::fmax;
 using std::fmin;
 using std::hypot;
+using std::pow;
 using std::sqrt;
 #endif
 
@@ -310,53 +311,6 @@ template <int m> struct PolyRoots {
     newton = a <= 0.02 * ax;
   }
 
-  // Largest real root of x^m + c[m-1] x^(m-1) + .. + c[0] from a warm start xg (the
-  // previous solve's root moved right by the caller's margin).  The Taylor
-  // coefficients of p at xg serve twice: all positive certifies that no real root
-  // lies to the right of xg (Budan-Fourier), and t0, t1, t2 = p, p', p''/2 give the
-  // first step for free — Halley's
-  //   a = p p' / (p'^2 - p p''/2)
-  // (cubic, one division, no square root; it lies between the Newton and the
-  // Laguerre step, so it is monotone in the same regime).  A step below 4e-7 |x|
-  // leaves an error ~ (step / |x|)^3 times the root's conditioning, i.e. rounding
-  // level for every root the caller goes on to certify: no polishing pass.
-  // Returns 1: root found; 0: certified, iterate() continues from x; -1: xg is not
-  // certified (or not given), the caller must start from a bound on the spectrum.
-  static EIG_FN int start(const double *c, double xg, double &x, bool &newton, double &root) {
-    if (!(xg > 0.))
-      return -1;
-    double t[m + 1];
-#pragma unroll
-    for (int k = 0; k < m; k++)
-      t[k] = c[k];
-    t[m] = 1.;
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < m; i++) {
-#pragma unroll
-      for (int k = m - 1; k >= i; k--)
-        t[k] = fma(xg, t[k + 1], t[k]);
-      ok = ok && (t[i] > 0.);
-    }
-    if (!ok)
-      return -1;
-    x = xg;
-    newton = false;
-    // (t0, t1 > 0 here; den <= 0, an overflow or a NaN leave the step to iterate())
-    const double den = fma(t[1], t[1], -(t[0] * t[2]));
-    const double a = (t[0] * t[1]) * (1. / den);
-    if (den > 0. && a <= 1e300) {
-      x = xg - a;
-      const double ax = fabs(x);
-      if (a <= 4e-7 * ax) {
-        root = x;
-        return 1;
-      }
-      newton = a <= 0.02 * ax;
-    }
-    return 0;
-  }
-
   // The monotone iteration from x, right of the largest real root.  false = fall back to QR.
   static EIG_FN bool iterate(const double *c, double x, bool newton, double &root) {
     int state = 0;
@@ -372,10 +326,10 @@ EIG_FN double pair_modulus2(double mu, double b1, double b0) {
   return re * re + (b0 - 0.25 * b1 * b1);
 }
 
-template <int n>
-EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess = nullptr) {
-  // shift by the mean eigenvalue
-  double mu = 0.;
+// Phase 1: mean shift mu = tr A / n and the coefficients of the characteristic
+// polynomial p(y) = y^n + c[n-1] y^(n-1) + .. + c[0] of B = A - mu I (c[n-1] = 0).
+template <int n> EIG_FN void poly_setup(const double *A, double &mu, double *c) {
+  mu = 0.;
 #pragma unroll
   for (int i = 0; i < n; i++)
     mu += A[i * n + i];
@@ -386,7 +340,6 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
 #pragma unroll
     for (int j = 0; j < n; j++)
       B[i * n + j] = A[i * n + j] - (i == j ? mu : 0.);
-  double c[n];
   c[n - 1] = 0.;
   if (n == 3) {
     // p(y) = y^3 + c1 y + c0: c1 = sum of principal 2 x 2 minors, c0 = -det B
@@ -468,67 +421,13 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
     }
   }
   }
+}
 
-  // Starting points.  Warm: the previous solve's outer roots moved outwards by four
-  // times the last observed change of the roots (a sequence of nearby states), within
-  // [1e-7, 1e-3] relative; first solve of a sequence: the Laguerre-Samuelson bound
-  // sqrt((n-1)/n sum y_i^2) = sqrt(-2 c_{n-2} (n-1)/n) of a real zero-mean spectrum.
-  // Either is used only under the Budan-Fourier certificate inside from_guess();
-  // the unconditional start is ||B||_inf, which bounds every root and is computed
-  // only when a certificate fails.
-  double xgp = -1., xgm = -1.;
-  if (guess && guess->valid) {
-    const double gp = guess->yp, gm = -guess->ym, d4 = 4. * guess->dy;
-    const double lp = 1e-7 * gp, hp = 1e-3 * gp, lm = 1e-7 * gm, hm = 1e-3 * gm;
-    xgp = gp + (d4 > hp ? hp : (d4 > lp ? d4 : lp)); // (plain selects: no NaN handling needed)
-    xgm = gm + (d4 > hm ? hm : (d4 > lm ? d4 : lm));
-  } else if (c[n - 2] < 0.) {
-    xgp = xgm = sqrt(-2. * c[n - 2] * ((n - 1.) / n)) * (1. + 1e-3);
-  }
-  // outermost real roots of the undeflated polynomial; the leftmost root of p is
-  // minus the rightmost root of (-1)^n p(-y)
-  double cm[n];
-#pragma unroll
-  for (int k = 0; k < n; k++)
-    cm[k] = ((n - k) & 1) ? -c[k] : c[k];
-  double yp, ym, xp = 0., xm = 0.;
-  bool np = false, nm = false;
-  int sp = PolyRoots<n>::start(c, xgp, xp, np, yp);
-  int sm = PolyRoots<n>::start(cm, xgm, xm, nm, ym);
-  if (sp < 0 || sm < 0) {
-    double R = 0.;
-#pragma unroll
-    for (int i = 0; i < n; i++) {
-      double rs = 0.;
-#pragma unroll
-      for (int j = 0; j < n; j++)
-        rs += fabs(B[i * n + j]);
-      R = fmax(R, rs);
-    }
-    if (!(R <= 1e150)) // NaN or huge: leave it to the general routine
-      return false;
-    if (R == 0.) {
-      rho = fabs(mu);
-      return true;
-    }
-    if (sp < 0) {
-      xp = R * (1. + 1e-12);
-      np = false;
-      sp = 0;
-    }
-    if (sm < 0) {
-      xm = R * (1. + 1e-12);
-      nm = false;
-      sm = 0;
-    }
-  }
-  if (sp == 0)
-    sp = PolyRoots<n>::iterate(c, xp, np, yp) ? 1 : 2;
-  if (sp == 1 && sm == 0)
-    sm = PolyRoots<n>::iterate(cm, xm, nm, ym) ? 1 : 2;
-  if (sp != 1 || sm != 1)
-    return false;
-  ym = -ym;
+// Phase 3: given the outermost real roots yp >= ym of p, certify that the spectral
+// radius |mu + y| is attained by one of them and update the warm-start record.
+template <int n>
+EIG_FN bool poly_finish(double mu, const double *c, double yp, double ym, double &rho,
+                        EigGuess *guess) {
   // both searches ending on the same root means a single real root (n odd) or a
   // multiple one
   const double ayp = fabs(yp), aym = fabs(ym);
@@ -625,6 +524,168 @@ EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess =
   return true;
 }
 
+// A bound on every root of p from its coefficients alone (Fujiwara):
+// |y| <= 2 max_k |c_{n-k}|^(1/k), with c_0 halved.  Only the rare searches whose
+// warm start is not certified start from here.  0 means p = y^n.
+template <int n> EIG_FN double poly_root_bound(const double *c) {
+  double b = 0.;
+#pragma unroll
+  for (int k = 1; k <= n; k++) {
+    const double ck = fabs(c[n - k]) * (k == n ? 0.5 : 1.);
+    const double r = k == 1 ? ck : (k == 2 ? sqrt(ck) : (k == 3 ? cbrt(ck) : (k == 4 ? sqrt(sqrt(ck)) : pow(ck, 1. / k))));
+    b = r > b ? r : b; // (a NaN coefficient: caught by the caller's range check on p)
+    if (!(ck <= 1e300))
+      b = ck;
+  }
+  return 2. * b;
+}
+
+// Phase 2 + 3 for NS independent polynomials at once (NS = 2: the left and the right
+// state of a face point).  The 2 NS root searches (largest root of p and of
+// (-1)^n p(-y) per side) take their certified warm-start step in lockstep —
+// straight-line code over independent dependency chains, which is what the FP64
+// pipe needs with four warps per scheduler — and only the searches that have not
+// converged by then continue one by one.  ok[s] = false: side s is left to the
+// general QR iteration.
+template <int n, int NS>
+EIG_FN void poly_solve(const double *mu, const double (*c)[n], EigGuess *const *guess, double *rho,
+                       bool *ok) {
+  constexpr int NC = 2 * NS;
+  double cc[NC][n], xg[NC];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+#pragma unroll
+    for (int k = 0; k < n; k++) {
+      cc[2 * s][k] = c[s][k];
+      cc[2 * s + 1][k] = ((n - k) & 1) ? -c[s][k] : c[s][k];
+    }
+    // Starting points.  Warm: the previous solve's outer roots moved outwards by four
+    // times the last observed change of the roots (a sequence of nearby states), within
+    // [1e-7, 1e-3] relative; first solve of a sequence: the Laguerre-Samuelson bound
+    // sqrt((n-1)/n sum y_i^2) = sqrt(-2 c_{n-2} (n-1)/n) of a real zero-mean spectrum.
+    // Either is used only under the Budan-Fourier certificate below.
+    xg[2 * s] = xg[2 * s + 1] = -1.;
+    const EigGuess *g = guess[s];
+    if (g && g->valid) {
+      const double gp = g->yp, gm = -g->ym, d4 = 4. * g->dy;
+      const double lp = 1e-7 * gp, hp = 1e-3 * gp, lm = 1e-7 * gm, hm = 1e-3 * gm;
+      xg[2 * s] = gp + (d4 > hp ? hp : (d4 > lp ? d4 : lp)); // (plain selects: no NaNs here)
+      xg[2 * s + 1] = gm + (d4 > hm ? hm : (d4 > lm ? d4 : lm));
+    } else if (c[s][n - 2] < 0.) {
+      xg[2 * s] = xg[2 * s + 1] = sqrt(-2. * c[s][n - 2] * ((n - 1.) / n)) * (1. + 1e-3);
+    }
+  }
+  // The Taylor coefficients of p at xg serve twice: all positive certifies that no real
+  // root lies to the right of xg (Budan-Fourier), and t0, t1, t2 = p, p', p''/2 give the
+  // first step for free — Halley's a = p p' / (p'^2 - p p''/2) (cubic, one reciprocal, no
+  // square root; it lies between the Newton and the Laguerre step, so it is monotone in
+  // the same regime).  A step below 4e-7 |x| leaves an error ~ (step / |x|)^3 times the
+  // root's conditioning, i.e. rounding level for every root poly_finish certifies.
+  double t[NC][n + 1];
+  bool cert[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+#pragma unroll
+    for (int j = 0; j < n; j++)
+      t[k][j] = cc[k][j];
+    t[k][n] = 1.;
+    cert[k] = xg[k] > 0.;
+  }
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+#pragma unroll
+    for (int j = n - 1; j >= i; j--)
+#pragma unroll
+      for (int k = 0; k < NC; k++)
+        t[k][j] = fma(xg[k], t[k][j + 1], t[k][j]);
+#pragma unroll
+    for (int k = 0; k < NC; k++)
+      cert[k] = cert[k] && (t[k][i] > 0.);
+  }
+  double den[NC], step[NC];
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    den[k] = fma(t[k][1], t[k][1], -(t[k][0] * t[k][2]));
+#pragma unroll
+  for (int k = 0; k < NC; k++)
+    step[k] = (t[k][0] * t[k][1]) * (1. / den[k]);
+  double x[NC], root[NC];
+  bool newton[NC];
+  int st[NC]; // 1 root found, 0 iterate from x, -1 start from a bound, 2 failed
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+    x[k] = xg[k];
+    root[k] = 0.;
+    newton[k] = false;
+    st[k] = cert[k] ? 0 : -1;
+    // (t0, t1 > 0 when certified; den <= 0, an overflow or a NaN leave it to iterate())
+    if (cert[k] && den[k] > 0. && step[k] <= 1e300) {
+      x[k] = xg[k] - step[k];
+      const double ax = fabs(x[k]);
+      if (step[k] <= 4e-7 * ax) {
+        root[k] = x[k];
+        st[k] = 1;
+      }
+      newton[k] = step[k] <= 0.02 * ax;
+    }
+  }
+  bool zero[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++)
+    zero[s] = false;
+#pragma unroll
+  for (int k = 0; k < NC; k++) {
+    if (st[k] < 0) {
+      const double bnd = poly_root_bound<n>(cc[k]);
+      if (bnd == 0.) {
+        zero[k / 2] = true; // p = y^n: every eigenvalue equals mu
+        st[k] = 1;
+      } else if (!(bnd <= 1e150)) {
+        st[k] = 2; // NaN or huge: leave it to the general routine
+      } else {
+        x[k] = bnd * (1. + 1e-12);
+        newton[k] = false;
+        st[k] = 0;
+      }
+    }
+    if (st[k] == 0)
+      st[k] = PolyRoots<n>::iterate(cc[k], x[k], newton[k], root[k]) ? 1 : 2;
+  }
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    if (zero[s]) {
+      rho[s] = fabs(mu[s]);
+      ok[s] = true;
+    } else {
+      ok[s] = st[2 * s] == 1 && st[2 * s + 1] == 1 &&
+              poly_finish<n>(mu[s], c[s], root[2 * s], -root[2 * s + 1], rho[s], guess[s]);
+    }
+  }
+}
+
+template <int n>
+EIG_FN bool spectral_radius_poly(const double *A, double &rho, EigGuess *guess = nullptr) {
+  double mu[1], c[1][n], r[1];
+  bool ok[1];
+  EigGuess *g[1] = {guess};
+  poly_setup<n>(A, mu[0], c[0]);
+  poly_solve<n, 1>(mu, c, g, r, ok);
+  rho = r[0];
+  return ok[0];
+}
+
+// Two matrices at once (the left and the right state of a face point): ok[s] = false
+// leaves side s to the caller's general routine.
+template <int n>
+EIG_FN void spectral_radius_poly_pair(const double *A0, const double *A1, double *rho, bool *ok,
+                                      EigGuess *g0, EigGuess *g1) {
+  double mu[2], c[2][n];
+  EigGuess *g[2] = {g0, g1};
+  poly_setup<n>(A0, mu[0], c[0]);
+  poly_setup<n>(A1, mu[1], c[1]);
+  poly_solve<n, 2>(mu, c, g, rho, ok);
+}
+
 // Parlett-Reinsch balancing by powers of two (an exact similarity): brings row
 // and column norms together so that conserved-variable Jacobians, whose entries
 // span orders of magnitude at high Mach number, lose nothing in either path.
@@ -670,6 +731,18 @@ template <int n> EIG_FN void balance(double *a) {
   }
 }
 
+// The general routine: balancing + QR iteration.  Only here does the matrix need an
+// address (the QR iteration indexes it dynamically); copying with static indices
+// keeps the caller's `a` in registers.
+template <int n> EIG_FN double spectral_radius_general(const double *a) {
+  double tmp[n * n];
+#pragma unroll
+  for (int i = 0; i < n * n; i++)
+    tmp[i] = a[i];
+  balance<n>(tmp);
+  return spectral_radius_qr<n>(tmp);
+}
+
 template <int n>
 EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr) {
   if (n == 1)
@@ -697,14 +770,7 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
     *path = 0;
   if (guess)
     guess->valid = 0;
-  // cold path: only here does the matrix need an address (the QR iteration indexes
-  // it dynamically); copying with static indices keeps the caller's `a` in registers
-  double tmp[n * n];
-#pragma unroll
-  for (int i = 0; i < n * n; i++)
-    tmp[i] = a[i];
-  balance<n>(tmp);
-  return spectral_radius_qr<n>(tmp);
+  return spectral_radius_general<n>(a);
 }
 
 // ---------------------------------------------------------------------------

@@ -62,3 +62,37 @@ extern "C" int pypde_b200_host_abs_matrix_apply(const double *A, int n, const do
 #undef CASE
   return ok ? 0 : 2;
 }
+
+// Two matrices through the two-sided polynomial path (what k_faces_fused runs per face
+// point); ok[s] = 0 where that path defers to the QR iteration (rho[s] then comes from it).
+extern "C" int pypde_b200_host_spectral_radius_pair(const double *A0, const double *A1, int n,
+                                                    double *rho, int *ok) {
+  if (n < 3 || n > 5 || !A0 || !A1 || !rho || !ok)
+    return 1;
+  bool k[2] = {false, false};
+  EigGuess g0{0., 0., 0., 0}, g1{0., 0., 0., 0};
+  switch (n) {
+  case 3:
+    spectral_radius_poly_pair<3>(A0, A1, rho, k, &g0, &g1);
+    spectral_radius_poly_pair<3>(A0, A1, rho, k, &g0, &g1); // second pass: warm
+    break;
+  case 4:
+    spectral_radius_poly_pair<4>(A0, A1, rho, k, &g0, &g1);
+    spectral_radius_poly_pair<4>(A0, A1, rho, k, &g0, &g1);
+    break;
+  case 5:
+    spectral_radius_poly_pair<5>(A0, A1, rho, k, &g0, &g1);
+    spectral_radius_poly_pair<5>(A0, A1, rho, k, &g0, &g1);
+    break;
+  }
+  const double *A[2] = {A0, A1};
+  for (int s = 0; s < 2; s++) {
+    ok[s] = k[s];
+    if (!k[s]) {
+      std::vector<double> a(A[s], A[s] + (size_t)n * n);
+      int pth;
+      pypde_b200_host_spectral_radius(a.data(), n, 1, &rho[s], &pth);
+    }
+  }
+  return 0;
+}

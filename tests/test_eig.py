@@ -169,6 +169,31 @@ def test_warm_start_gives_the_cold_result():
                 assert fast > 500
 
 
+def test_two_sided_path():
+    """The left / right pair entry (lockstep root searches of both matrices, cold pass
+    then warm pass) returns what the one-matrix entry returns for each of them."""
+    lib = get_cdll()
+    rng = np.random.default_rng(12)
+    for n in (3, 4, 5):
+        fast = 0
+        for it in range(400):
+            kinds = ('euler', 'real', 'complex_dominant', 'complex_small')
+            D0, t0 = spectrum_case(n, kinds[it % 2], rng)
+            D1, t1 = spectrum_case(n, kinds[(it // 2) % 4], rng)
+            A0, A1 = similar(D0, rng), similar(D1, rng)
+            r = (ctypes.c_double * 2)()
+            ok = (ctypes.c_int * 2)()
+            rc = lib.pypde_b200_host_spectral_radius_pair(
+                np.ascontiguousarray(A0).ctypes.data_as(P), np.ascontiguousarray(A1).ctypes.data_as(P),
+                n, r, ok)
+            assert rc == 0
+            fast += ok[0] + ok[1]
+            for val, A, true in ((r[0], A0, t0), (r[1], A1, t1)):
+                assert abs(val - rho(A)[0]) <= 1e-13 * true
+                assert abs(val - true) / true < 2e-13
+        assert fast > 400
+
+
 def abs_apply(A, x):
     lib = get_cdll()
     A = np.ascontiguousarray(A, dtype=float)

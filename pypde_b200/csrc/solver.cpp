@@ -303,6 +303,12 @@ Solver::~Solver() {
     d.StreamSynchronize(copy_stream_);
     d.StreamDestroy(copy_stream_);
   }
+  if (comm_stream_) {
+    d.StreamSynchronize(comm_stream_);
+    d.StreamDestroy(comm_stream_);
+    d.EventDestroy(ev_edge_);
+    d.EventDestroy(ev_halo_);
+  }
   if (stream_)
     d.StreamSynchronize(stream_);
   if (own_stream_ && stream_)
@@ -315,6 +321,8 @@ void Solver::set_stream(CUstream s) {
   const DriverApi &d = driver();
   if (stream_)
     check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+  if (comm_stream_)
+    check(d.StreamSynchronize(comm_stream_), "cuStreamSynchronize(comm)");
   if (own_stream_ && stream_)
     d.StreamDestroy(stream_);
   stream_ = s;
@@ -331,6 +339,7 @@ void Solver::set_state(const double *u_host) {
   check(d.MemcpyHtoDAsync(u_, u_host, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
         "cuMemcpyHtoDAsync(u)");
   check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
+  halo_valid_ = false;
 }
 
 void Solver::get_state(double *u_host) {
@@ -346,6 +355,7 @@ void Solver::get_state(double *u_host) {
 void Solver::bind_state(CUdeviceptr u) {
   u_own_.release();
   u_ = u;
+  halo_valid_ = false;
 }
 
 void Solver::snapshot_prev() {
@@ -375,6 +385,7 @@ void Solver::begin(double tf) {
   s.tf = tf;
   s.cfl = cfl_;
   *h_state_ = s;
+  halo_valid_ = false; // the caller may have written the (bound) state since the last step
   const DriverApi &d = driver();
   check(d.MemcpyHtoDAsync(state_.p, h_state_, sizeof(StepState), stream_), "cuMemcpyHtoDAsync(state)");
   check(d.StreamSynchronize(stream_), "cuStreamSynchronize");
@@ -466,10 +477,19 @@ double Solver::measure_fp64_peak() {
   return best;
 }
 
-void Solver::exchange_halos() {
+void Solver::post_halo_exchange() {
   const Comm &cm = global_comm();
   if (cm.nranks <= 1)
     return;
+  const DriverApi &d = driver();
+  if (!comm_stream_) {
+    check(d.StreamCreate(&comm_stream_, CU_STREAM_NON_BLOCKING), "cuStreamCreate(comm)");
+    check(d.EventCreate(&ev_edge_, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+    check(d.EventCreate(&ev_halo_, CU_EVENT_DISABLE_TIMING), "cuEventCreate");
+  }
+  // the edge rows are final at this point of the compute stream
+  check(d.EventRecord(ev_edge_, stream_), "cuEventRecord(edge)");
+  check(d.StreamWaitEvent(comm_stream_, ev_edge_, 0), "cuStreamWaitEvent(edge)");
   const NcclApi &nc = nccl();
   const int N = cfg_.N, V = cfg_.V;
   const size_t cnt = (size_t)N * rowlen_ * V;
@@ -488,14 +508,26 @@ void Solver::exchange_halos() {
   // posting order, so the peer's "first rows" must meet our high-halo receive.
   ok(nc.GroupStart(), "ncclGroupStart");
   if (lo >= 0)
-    ok(nc.Send((const void *)first_rows, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclSend");
+    ok(nc.Send((const void *)first_rows, cnt, NCCL_FLOAT64, lo, cm.comm, comm_stream_), "ncclSend");
   if (hi >= 0)
-    ok(nc.Send((const void *)last_rows, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclSend");
+    ok(nc.Send((const void *)last_rows, cnt, NCCL_FLOAT64, hi, cm.comm, comm_stream_), "ncclSend");
   if (hi >= 0)
-    ok(nc.Recv((void *)halo_hi_.p, cnt, NCCL_FLOAT64, hi, cm.comm, stream_), "ncclRecv");
+    ok(nc.Recv((void *)halo_hi_.p, cnt, NCCL_FLOAT64, hi, cm.comm, comm_stream_), "ncclRecv");
   if (lo >= 0)
-    ok(nc.Recv((void *)halo_lo_.p, cnt, NCCL_FLOAT64, lo, cm.comm, stream_), "ncclRecv");
+    ok(nc.Recv((void *)halo_lo_.p, cnt, NCCL_FLOAT64, lo, cm.comm, comm_stream_), "ncclRecv");
   ok(nc.GroupEnd(), "ncclGroupEnd");
+  check(d.EventRecord(ev_halo_, comm_stream_), "cuEventRecord(halo)");
+  halo_valid_ = true;
+}
+
+void Solver::update_cells(long cell0, long ncells) {
+  if (ncells <= 0)
+    return;
+  FluxPtrs fp;
+  for (int i = 0; i < 3; i++)
+    fp.f[i] = flx_[i < cfg_.ndim ? i : 0].p;
+  void *args[] = {&u_, &centers_.p, &fp, &g_, &state_.p, &cell0, &ncells};
+  launch(mod_->k_update, grid_for(ncells * cfg_.V, 256), 256, 0, args, "k_update");
 }
 
 // runs the ndim sweeps; shape_in = padded shape of `in`; bufs[d] = output of sweep d
@@ -529,7 +561,14 @@ void Solver::step_async() {
   const int Nd = ipow(N, nd);
   const Comm &cm = global_comm();
 
-  exchange_halos();
+  if (cm.nranks > 1) {
+    // halos of the current state: posted at the end of the previous step (overlapped
+    // with its interior update), or here if the state was set since
+    if (!halo_valid_)
+      post_halo_exchange();
+    check(driver().StreamWaitEvent(stream_, ev_halo_, 0), "cuStreamWaitEvent(halo)");
+    halo_valid_ = false;
+  }
   {
     long total = 1;
     for (int i = 0; i < nd; i++)
@@ -621,12 +660,17 @@ void Solver::step_async() {
       launch(mod_->k_faces, (unsigned)nblocks, block, smem, args, "k_faces");
     }
   }
-  {
-    FluxPtrs fp;
-    for (int i = 0; i < 3; i++)
-      fp.f[i] = flx_[i < nd ? i : 0].p;
-    void *args[] = {&u_, &centers_.p, &fp, &g_, &state_.p};
-    launch(mod_->k_update, grid_for(ncell_ * V, 256), 256, 0, args, "k_update");
+  if (cm.nranks > 1 && g_.nX[0] >= 2 * N) {
+    // the N rows each neighbour needs first; their exchange then overlaps the rest
+    const long edge = (long)N * rowlen_;
+    update_cells(0, edge);
+    update_cells(ncell_ - edge, edge);
+    post_halo_exchange();
+    update_cells(edge, ncell_ - 2 * edge);
+  } else {
+    update_cells(0, ncell_);
+    if (cm.nranks > 1)
+      post_halo_exchange();
   }
   {
     void *args[] = {&state_.p};

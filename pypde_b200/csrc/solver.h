@@ -115,7 +115,17 @@ private:
   std::vector<Rec> recs_;
   unsigned grid_for(long total, unsigned block) const;
   void run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs);
-  void exchange_halos();
+  // Multi-GPU halos (axis 0).  post_halo_exchange() enqueues, on the communication
+  // stream, the send / receive of the N edge rows of u per side into halo_lo_/halo_hi_
+  // once the compute stream has reached the point where those rows are final; the next
+  // k_boundaries waits for it.  Inside a run the exchange is posted right after the edge
+  // rows' k_update and overlaps the interior rows' update (and whatever the caller
+  // enqueues between steps); halo_valid_ = false forces one at the start of a step.
+  void post_halo_exchange();
+  void update_cells(long cell0, long ncells);
+  CUstream comm_stream_ = nullptr;
+  CUevent ev_edge_ = nullptr, ev_halo_ = nullptr;
+  bool halo_valid_ = false;
 
   KernelConfig cfg_;
   std::shared_ptr<Module> mod_;

@@ -383,9 +383,11 @@ def main():
                'h2d_bytes_per_step': Q0.nbytes / K,
                'd2h_bytes_per_step': (2 * Q0.nbytes + 56 * K) / K,
                'seconds': secs, 'steps': K,
-               'what': 'one pde_solver() C-ABI call from host Q0 to host ret for exactly K steps: '
-                       'kernel-module load, device alloc, H2D of Q0, K steps with a per-step '
-                       'sync + D2H of (t, dt), D2H of the final state into ret and Q0'}
+               'what': 'one pde_solver() C-ABI call from pinned host Q0 to host ret for exactly K '
+                       'steps (second call: the library keeps the solver — kernel module and '
+                       'work arrays — of the previous call with the same configuration): H2D of '
+                       'Q0, K steps with a per-step sync + D2H of (t, dt), D2H of the final '
+                       'state into ret and Q0'}
 
     # ---- CPU baseline beside it (rank 0, bounded sample)
     cpu = None

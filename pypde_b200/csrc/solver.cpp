@@ -119,6 +119,12 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   if (cfg_.flux < 0 || cfg_.flux > 2)
     throw std::runtime_error("pypde_b200: FLUX must be 0 (rusanov), 1 (roe) or 2 (osher)");
   choose_block_shapes(cfg_);
+  // k_faces_fused (both sides of a face point in one thread) wins where the eigen-solves
+  // stay in registers: small systems with a first-order flux.  Measured on B200: C2 (V = 4)
+  // 6.2 against 9.3 ms per step; GPR (V = 17) 19.9 against 13.4 ms and 3-D Navier-Stokes
+  // (second-order flux: gradient traces of both sides live at once) 20.5 against 12.9 ms
+  // for k_wavespeeds + k_faces.
+  fused_faces_ = cfg_.V <= 5 && !cfg_.secondOrder;
   if (const char *e = getenv("PYPDE_B200_FUSED_FACES"))
     fused_faces_ = *e != '0';
   if (const char *e = getenv("PYPDE_B200_DG_NODE"))
@@ -228,20 +234,6 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
       check(d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
                                (int)(stiff_wpb_ * smem_warp)),
             "cuFuncSetAttribute(k_dg_stiff smem)");
-  }
-  // the predictor kernels keep their working set in shared memory and run many small
-  // blocks per SM: ask for the largest shared-memory carve-out so that residency is
-  // bounded by registers, not by the driver's default L1 / shared split
-  {
-    int carve = 100; // percent of the maximum (CU_SHAREDMEM_CARVEOUT_MAX_SHARED)
-    if (const char *e = getenv("PYPDE_B200_DG_CARVEOUT"))
-      carve = atoi(e);
-    if (carve >= 0) {
-      d.FuncSetAttribute(mod_->k_dg, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, carve);
-      if (cfg_.stiff)
-        d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT,
-                           carve);
-    }
   }
   // dynamic shared memory opt-in
   const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;

@@ -90,6 +90,27 @@ def test_solver_golden(golden, name):
     assert np.array_equal(Q0, out[-1])       # in-place update of Q0, as the reference
 
 
+@pytest.mark.parametrize('name,env', [
+    ('euler2d_explosion_N3', 'PYPDE_B200_DG_NODE'), ('sod_N2', 'PYPDE_B200_DG_NODE'),
+    ('euler3d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('burgers2d_N2', 'PYPDE_B200_DG_NODE'),
+    ('euler2d_explosion_N3', 'PYPDE_B200_FUSED_FACES'), ('sod_N2', 'PYPDE_B200_FUSED_FACES'),
+    ('euler3d_smooth_N2', 'PYPDE_B200_FUSED_FACES')])
+def test_kernel_variants_agree_bit_for_bit(name, env):
+    """The node-thread predictor (k_dg_n) and the fused Rusanov face kernel
+    (k_faces_fused) run every sum in the order of the general kernels they replace
+    (k_dg; k_wavespeeds + k_faces): same bits, whole runs."""
+    c = cases.solver_cases()[name]
+    outs = []
+    for val in ('1', '0'):
+        # (the switches are read when a solver is built: do not reuse the cached one)
+        os.environ[env], os.environ['PYPDE_B200_KEEP_SOLVER'] = val, '0'
+        try:
+            outs.append(run_gpu(c)[0])
+        finally:
+            del os.environ[env], os.environ['PYPDE_B200_KEEP_SOLVER']
+    assert np.array_equal(outs[0], outs[1])
+
+
 def test_ret_row_semantics():
     """iterator.cpp:136-139,150: at most one row per step; unreached rows stay
     zero; the last row is the final state."""

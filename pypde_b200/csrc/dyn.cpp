@@ -81,6 +81,7 @@ const DriverApi &driver() {
       B(EventSynchronize, "cuEventSynchronize");
       B(EventElapsedTime, "cuEventElapsedTime");
       B(StreamWaitEvent, "cuStreamWaitEvent");
+      B(TensorMapEncodeTiled, "cuTensorMapEncodeTiled");
 #undef B
       CUresult r = api.Init(0);
       if (r != CUDA_SUCCESS) {

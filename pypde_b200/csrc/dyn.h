@@ -48,6 +48,10 @@ struct DriverApi {
   CUresult (*EventSynchronize)(CUevent);
   CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
   CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
+  CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                   const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 };
 
 struct NvrtcApi {

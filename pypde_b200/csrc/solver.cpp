@@ -18,6 +18,24 @@ int ipow(int b, int e) {
 }
 } // namespace
 
+// tile of k_weno2d (kernels.cuh: W2_TJ, W2_TI, W2_OK); false where that kernel is not compiled
+bool weno2d_tile(const KernelConfig &c, int *ti_out, int *tj_out) {
+  if (c.ndim != 2)
+    return false;
+  const int H = 2 * (c.N - 1), N = c.N, V = c.V;
+  const int tj = V * (32 + H) <= 256 ? 32 : (V * (16 + H) <= 256 ? 16 : 8);
+  const int row = (tj + H) * V;
+  auto smem = [&](int ti) { return ((ti + H) * row + ti * (tj + H) * N * V) * 8 + 256; };
+  const int ti = smem(8) <= 48 * 1024 ? 8 : 4;
+  if (row > 256 || smem(ti) > 48 * 1024)
+    return false;
+  if (ti_out)
+    *ti_out = ti;
+  if (tj_out)
+    *tj_out = tj;
+  return true;
+}
+
 void check(CUresult r, const char *what) {
   if (r == CUDA_SUCCESS)
     return;
@@ -98,6 +116,8 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   // kernels.cuh: DGN_OK
   if (!cfg.useB && !cfg.secondOrder && cfg.N >= 2 && ipow(cfg.N, cfg.ndim) <= 32)
     get(k_dg_n, "k_dg_n");
+  if (weno2d_tile(cfg, nullptr, nullptr))
+    get(k_weno2d, "k_weno2d");
 }
 
 Module::~Module() {
@@ -200,6 +220,25 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     w_.alloc((size_t)ncellw_ * Nd * V * D);
   }
   traces_.alloc((size_t)ncellw_ * 2 * nd * NP * TRW * V * D);
+  // k_weno2d: TMA descriptor of ub as a 2-D tensor [nX_0+2N rows][(nX_1+2N) V doubles]
+  // (row pitch must be a multiple of 16 bytes; otherwise the two-sweep path stays)
+  if (weno2d_tile(cfg_, &weno2d_ti_, &weno2d_tj_) && mod_->k_weno2d) {
+    const char *e = getenv("PYPDE_B200_WENO_FUSED");
+    const cuuint64_t cols = (cuuint64_t)(nX[1] + 2 * N) * V, rows = (cuuint64_t)(nX[0] + 2 * N);
+    const int H = 2 * (N - 1);
+    if (!(e && *e == '0') && cols % 2 == 0 && d.TensorMapEncodeTiled) {
+      const cuuint64_t dims[2] = {cols, rows};
+      const cuuint64_t strides[1] = {cols * D};
+      const cuuint32_t box[2] = {(cuuint32_t)((weno2d_tj_ + H) * V), (cuuint32_t)(weno2d_ti_ + H)};
+      const cuuint32_t estr[2] = {1, 1};
+      CUresult r = d.TensorMapEncodeTiled(&ub_map_, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
+                                          (void *)ub_.p, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      weno2d_ = r == CUDA_SUCCESS;
+    }
+  }
   if (cfg_.useF) // per trace point: lambda, [lambda_visc]
     ws_.alloc((size_t)ncellw_ * 2 * nd * NP * (1 + (cfg_.secondOrder ? 1 : 0)) * D);
   centers_.alloc((size_t)ncellw_ * V * D);
@@ -394,7 +433,7 @@ unsigned Solver::grid_for(long total, unsigned block) const {
 }
 
 void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
-                    const char *name) {
+                    const char *name, unsigned grid_y) {
   const DriverApi &d = driver();
   Rec r{name, nullptr, nullptr};
   if (profiling_) {
@@ -402,7 +441,8 @@ void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, vo
     check(d.EventCreate(&r.b, CU_EVENT_DEFAULT), "cuEventCreate");
     check(d.EventRecord(r.a, stream_), "cuEventRecord");
   }
-  check(d.LaunchKernel(f, grid, 1, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr), name);
+  check(d.LaunchKernel(f, grid, grid_y, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr),
+        name);
   if (profiling_) {
     check(d.EventRecord(r.b, stream_), "cuEventRecord");
     recs_.push_back(r);
@@ -569,7 +609,12 @@ void Solver::step_async() {
     void *args[] = {&u_, &halo_lo_.p, &halo_hi_.p, &ub_.p, &g_};
     launch(mod_->k_boundaries, grid_for(total, 256), 256, 0, args, "k_boundaries");
   }
-  {
+  if (weno2d_) {
+    int n0 = g_.nX[0] + 2, n1 = g_.nX[1] + 2;
+    void *args[] = {&ub_map_, &w_.p, &n0, &n1};
+    launch(mod_->k_weno2d, (unsigned)((n0 + weno2d_ti_ - 1) / weno2d_ti_), 256, 0, args, "k_weno2d",
+           (unsigned)((n1 + weno2d_tj_ - 1) / weno2d_tj_));
+  } else {
     long shape[3];
     for (int i = 0; i < nd; i++)
       shape[i] = g_.nX[i] + 2 * N;

@@ -59,7 +59,8 @@ public:
   CUfunction k_fp64_peak = nullptr;
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
-             k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr, k_dg_n = nullptr;
+             k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr, k_dg_n = nullptr,
+             k_weno2d = nullptr;
 };
 
 class Solver {
@@ -106,7 +107,7 @@ public:
 
 private:
   void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
-              const char *name);
+              const char *name, unsigned grid_y = 1);
   bool profiling_ = false;
   struct Rec {
     const char *name;
@@ -140,6 +141,10 @@ private:
   DeviceBuffer stiff_work_;
   bool fused_faces_ = true;
   bool node_dg_ = true; // k_dg_n where it applies (PYPDE_B200_DG_NODE=0: always k_dg)
+  // 2-D: both WENO sweeps in one tiled kernel fed by TMA (PYPDE_B200_WENO_FUSED=0: two sweeps)
+  bool weno2d_ = false;
+  int weno2d_ti_ = 0, weno2d_tj_ = 0;
+  CUtensorMap ub_map_;
   int stiff_wpb_ = 4;
   long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,

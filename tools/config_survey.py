@@ -42,6 +42,13 @@ def run(name, system, Q0, L, N, bts, steps=4, warm=2, **kw):
 
 if __name__ == '__main__':
     big = len(sys.argv) > 1 and sys.argv[1] == 'big'
+    only = sys.argv[2].split(',') if len(sys.argv) > 2 else None   # e.g. C4,C5
+    if only:
+        _run = run
+
+        def run(name, *a, **kw):
+            if name[:2] in only:
+                _run(name, *a, **kw)
     n2 = 1024 if big else 256
     run('C1 1-D Euler Sod N=2', 'euler', cases.sod(200), [1.], 2, ['transitive'], steps=20)
     run('C2 2-D Euler explosion N=3', 'euler', cases.euler_explosion((n2, n2)), [1., 1.], 3,

@@ -636,9 +636,15 @@ EIG_FN void poly_solve(const double *mu, const double (*c)[n], EigGuess *const *
 #pragma unroll
   for (int k = 0; k < NC; k++) {
     if (st[k] < 0) {
-      const double bnd = poly_root_bound<n>(cc[k]);
-      if (bnd == 0.) {
-        zero[k / 2] = true; // p = y^n: every eigenvalue equals mu
+      // p = y^n (a zero matrix up to the shift, e.g. a flux without a gradient term in
+      // this direction): every eigenvalue equals mu
+      bool allzero = true;
+#pragma unroll
+      for (int j = 0; j < n; j++)
+        allzero = allzero && cc[k][j] == 0.;
+      const double bnd = allzero ? 0. : poly_root_bound<n>(cc[k]);
+      if (allzero) {
+        zero[k / 2] = true;
         st[k] = 1;
       } else if (!(bnd <= 1e150)) {
         st[k] = 2; // NaN or huge: leave it to the general routine

@@ -203,6 +203,10 @@ void choose_block_shapes(KernelConfig &c) {
     c.ws_block = atoi(e);
   if (const char *e = getenv("PYPDE_B200_WS_MINBLOCKS"))
     c.ws_minblocks = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_FF_BLOCK"))
+    c.ff_block = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_FF_MINBLOCKS"))
+    c.ff_minblocks = atoi(e);
   if (const char *e = getenv("PYPDE_B200_DG_CPB"))
     c.dg_cpb = atoi(e);
   if (const char *e = getenv("PYPDE_B200_FACES_FPB"))
@@ -230,7 +234,9 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_FACES_FPB", c.faces_fpb),
           kv("PDE_STIFF_WPB", c.stiff_wpb),
           kv("PDE_WS_BLOCK", c.ws_block),
-          kv("PDE_WS_MINBLOCKS", c.ws_minblocks)};
+          kv("PDE_WS_MINBLOCKS", c.ws_minblocks),
+          kv("PDE_FF_BLOCK", c.ff_block),
+          kv("PDE_FF_MINBLOCKS", c.ff_minblocks)};
   // tuning experiments: PYPDE_B200_EXTRA_DEFINES="PDE_X=1;PDE_Y=0"
   if (const char *e = getenv("PYPDE_B200_EXTRA_DEFINES")) {
     std::string all(e);

@@ -674,7 +674,7 @@ void Solver::step_async() {
   if (cfg_.useF && cfg_.flux == 0 && fused_faces_) {
     for (int dd = 0; dd < nd; dd++) {
       void *args[] = {&traces_.p, &flx_[dd].p, &dd, &nfaces_[dd], &g_, &state_.p};
-      launch(mod_->k_faces_fused, grid_for(nfaces_[dd], cfg_.ws_block), cfg_.ws_block, 0, args,
+      launch(mod_->k_faces_fused, grid_for(nfaces_[dd], cfg_.ff_block), cfg_.ff_block, 0, args,
              "k_faces_fused");
     }
   } else if (cfg_.useF && cfg_.flux == 0) {

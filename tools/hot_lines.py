@@ -84,7 +84,9 @@ if __name__ == '__main__':
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
     hdr, rows = ncu_instr(rep, kernel)
     lt = line_table(cubin, kernel)
-    body = source_lines(2, 3, 4)
+    import os
+    _c = [int(x) for x in os.environ.get("HOT_LINES_CFG", "2,3,4,1,0,0,0").split(",")]
+    body = source_lines(*_c)
     ie = hdr.index('Instructions Executed')
     isamp = hdr.index('# Samples')
     print('%s: %d SASS instructions in report, %d in local cubin' % (kernel, len(rows), len(lt)))

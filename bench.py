@@ -71,6 +71,7 @@ def algorithmic_model(n):
     s0 = ((n + 2 * N)**2 + (n + 2) * (n + 2 * N) * N) * V * D
     s1 = ((n + 2) * (n + 2 * N) * N + cw * Nd) * V * D
     kb['k_weno_sweep'] = (s0 + s1) / 2.
+    kb['k_weno2d'] = ((n + 2 * N)**2 + cw * Nd) * V * D                # ub in, w out
     # SURVEY 8d three-product model: 8 V (3 + 2 Nd + 2 N Nd) bytes per cell-update
     b_alg = 8 * V * (3 + 2 * Nd + 2 * N * Nd)
     f_alg = 4.5e4   # flop per cell-update at this config, ~70% in the face eigen-solves

@@ -249,6 +249,17 @@ struct EigGuess {
   int valid;
 };
 
+template <int n> struct PolyCoef { // coefficients by value: for the out-of-line cold paths
+  double v[n];
+};
+struct PolyIterResult {
+  double root;
+  int ok;
+};
+#ifndef PDE_EIG_ITER_NOINLINE
+#define PDE_EIG_ITER_NOINLINE 0 // (1: measured neutral on B200 at C2)
+#endif
+
 template <int m> struct PolyRoots {
   // One monotone step towards the largest real root from a point to its right:
   // Laguerre's iteration in the one-division form
@@ -317,6 +328,14 @@ template <int m> struct PolyRoots {
     for (int it = 0; it < 30 && state == 0; it++)
       step(c, x, newton, state, root);
     return state == 1;
+  }
+  // The same out of line (arguments by value, so the caller's coefficients stay in
+  // registers): searches that the warm Halley step did not finish.
+  static EIG_FN_NOINLINE PolyIterResult iterate_call(PolyCoef<m> pc, double x, bool newton) {
+    PolyIterResult r;
+    r.root = 0.;
+    r.ok = iterate(pc.v, x, newton, r.root) ? 1 : 0;
+    return r;
   }
 };
 
@@ -527,7 +546,8 @@ EIG_FN bool poly_finish(double mu, const double *c, double yp, double ym, double
 // A bound on every root of p from its coefficients alone (Fujiwara):
 // |y| <= 2 max_k |c_{n-k}|^(1/k), with c_0 halved.  Only the rare searches whose
 // warm start is not certified start from here.  0 means p = y^n.
-template <int n> EIG_FN double poly_root_bound(const double *c) {
+template <int n> EIG_FN_NOINLINE double poly_root_bound(PolyCoef<n> pc) {
+  const double *c = pc.v;
   double b = 0.;
 #pragma unroll
   for (int k = 1; k <= n; k++) {
@@ -642,7 +662,14 @@ EIG_FN void poly_solve(const double *mu, const double (*c)[n], EigGuess *const *
 #pragma unroll
       for (int j = 0; j < n; j++)
         allzero = allzero && cc[k][j] == 0.;
-      const double bnd = allzero ? 0. : poly_root_bound<n>(cc[k]);
+      double bnd = 0.;
+      if (!allzero) {
+        PolyCoef<n> pc;
+#pragma unroll
+        for (int j = 0; j < n; j++)
+          pc.v[j] = cc[k][j];
+        bnd = poly_root_bound<n>(pc);
+      }
       if (allzero) {
         zero[k / 2] = true;
         st[k] = 1;
@@ -654,8 +681,19 @@ EIG_FN void poly_solve(const double *mu, const double (*c)[n], EigGuess *const *
         st[k] = 0;
       }
     }
-    if (st[k] == 0)
+    if (st[k] == 0) {
+#if PDE_EIG_ITER_NOINLINE
+      PolyCoef<n> pc;
+#pragma unroll
+      for (int j = 0; j < n; j++)
+        pc.v[j] = cc[k][j];
+      const PolyIterResult ir = PolyRoots<n>::iterate_call(pc, x[k], newton[k]);
+      root[k] = ir.root;
+      st[k] = ir.ok ? 1 : 2;
+#else
       st[k] = PolyRoots<n>::iterate(cc[k], x[k], newton[k], root[k]) ? 1 : 2;
+#endif
+    }
   }
 #pragma unroll
   for (int s = 0; s < NS; s++) {
@@ -740,13 +778,18 @@ template <int n> EIG_FN void balance(double *a) {
 // The general routine: balancing + QR iteration.  Only here does the matrix need an
 // address (the QR iteration indexes it dynamically); copying with static indices
 // keeps the caller's `a` in registers.
+template <int n> EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a) {
+  balance<n>(a);
+  return spectral_radius_qr<n>(a);
+}
 template <int n> EIG_FN double spectral_radius_general(const double *a) {
+  // (everything cold stays out of line: ncu showed the hot path's instruction fetches
+  //  stalling at the reconvergence points behind inlined cold blocks)
   double tmp[n * n];
 #pragma unroll
   for (int i = 0; i < n * n; i++)
     tmp[i] = a[i];
-  balance<n>(tmp);
-  return spectral_radius_qr<n>(tmp);
+  return spectral_radius_balanced_qr<n>(tmp);
 }
 
 template <int n>

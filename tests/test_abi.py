@@ -75,7 +75,17 @@ def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
     assert 'sm_100' in elf or 'SM100' in elf.upper()
     for k in ['k_boundaries', 'k_weno_sweep', 'k_cfl', 'k_dt', 'k_dg', 'k_wavespeeds', 'k_faces',
               'k_update']:
-        assert 'Function %s' % k in out, k
+        assert 'Function %s:' % k in out, k
+    # the specialised kernels exist exactly where the host driver looks for them
+    # (solver.cpp: Module::Module): the node-thread predictor without gradient terms in the
+    # predictor, the fused Rusanov face kernel, the TMA-fed two-sweep WENO tile kernel in 2-D
+    first_order_no_B = B is None and not getattr(F, 'second_order', False)
+    assert ('Function k_dg_n:' in out) == (first_order_no_B and N >= 2 and N**ndim <= 32)
+    assert 'Function k_faces_fused:' in out
+    assert ('Function k_weno2d:' in out) == (ndim == 2)
+    if ndim == 2:
+        sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', 'k_weno2d', path]).decode()
+        assert 'UTMALDG' in sass and 'SYNCS' in sass      # TMA bulk-tensor load + mbarrier
 
 
 def test_jit_reports_user_function_errors():

@@ -1,5 +1,6 @@
 #!/bin/bash
-# end-of-session evidence run on one B200: parity suite, smoke, both bench arms, launch list, ncu --set full
+# end-of-round evidence run on one B200 (gpurun -- tools/evidence_run.sh): parity suite, smoke, both bench arms,
+# launch list, ncu --set full of the main kernels, parity table, config survey; outputs under gpurun_out/
 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/f_pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 > gpurun_out/f_smoke.log
 python bench.py --impl reference 2>&1 | tail -1 > gpurun_out/f_bench_ref.json

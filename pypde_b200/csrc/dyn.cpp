@@ -82,6 +82,12 @@ const DriverApi &driver() {
       B(EventElapsedTime, "cuEventElapsedTime");
       B(StreamWaitEvent, "cuStreamWaitEvent");
       B(TensorMapEncodeTiled, "cuTensorMapEncodeTiled");
+      B(StreamBeginCapture, "cuStreamBeginCapture_v2");
+      B(StreamEndCapture, "cuStreamEndCapture");
+      B(GraphInstantiate, "cuGraphInstantiateWithFlags");
+      B(GraphLaunch, "cuGraphLaunch");
+      B(GraphExecDestroy, "cuGraphExecDestroy");
+      B(GraphDestroy, "cuGraphDestroy");
 #undef B
       CUresult r = api.Init(0);
       if (r != CUDA_SUCCESS) {

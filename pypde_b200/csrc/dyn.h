@@ -48,6 +48,12 @@ struct DriverApi {
   CUresult (*EventSynchronize)(CUevent);
   CUresult (*EventElapsedTime)(float *, CUevent, CUevent);
   CUresult (*StreamWaitEvent)(CUstream, CUevent, unsigned);
+  CUresult (*StreamBeginCapture)(CUstream, CUstreamCaptureMode);
+  CUresult (*StreamEndCapture)(CUstream, CUgraph *);
+  CUresult (*GraphInstantiate)(CUgraphExec *, CUgraph, unsigned long long);
+  CUresult (*GraphLaunch)(CUgraphExec, CUstream);
+  CUresult (*GraphExecDestroy)(CUgraphExec);
+  CUresult (*GraphDestroy)(CUgraph);
   CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,

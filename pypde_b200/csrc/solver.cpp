@@ -149,6 +149,14 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     fused_faces_ = *e != '0';
   if (const char *e = getenv("PYPDE_B200_DG_NODE"))
     node_dg_ = *e != '0';
+  {
+    long cells = 1;
+    for (int i = 0; i < cfg_.ndim; i++)
+      cells *= nX[i];
+    graph_enabled_ = cells <= 65536; // beyond that a step is milliseconds of kernels
+    if (const char *e = getenv("PYPDE_B200_GRAPH"))
+      graph_enabled_ = *e != '0';
+  }
   ensure_context();
   const DriverApi &d = driver();
   CUdevice dev;
@@ -320,6 +328,9 @@ void Solver::drain_snapshots() {
 
 Solver::~Solver() {
   const DriverApi &d = driver();
+  if (stream_)
+    d.StreamSynchronize(stream_);
+  drop_graph();
   for (SnapSlot &s : snap_) {
     if (s.dst && s.done)
       d.EventSynchronize(s.done);
@@ -358,6 +369,7 @@ void Solver::set_stream(CUstream s) {
     d.StreamDestroy(stream_);
   stream_ = s;
   own_stream_ = false;
+  drop_graph();
 }
 
 void Solver::set_state(const double *u_host) {
@@ -365,6 +377,7 @@ void Solver::set_state(const double *u_host) {
   if (!u_) {
     u_own_.alloc((size_t)ncell_ * cfg_.V * sizeof(double));
     u_ = u_own_.p;
+    drop_graph();
   }
   const DriverApi &d = driver();
   check(d.MemcpyHtoDAsync(u_, u_host, (size_t)ncell_ * cfg_.V * sizeof(double), stream_),
@@ -387,6 +400,7 @@ void Solver::bind_state(CUdeviceptr u) {
   u_own_.release();
   u_ = u;
   halo_valid_ = false;
+  drop_graph(); // the graph holds the state pointer
 }
 
 void Solver::snapshot_prev() {
@@ -587,8 +601,45 @@ void Solver::run_sweeps(CUdeviceptr in, const long *shape_in, CUdeviceptr *bufs)
   }
 }
 
+void Solver::drop_graph() {
+  if (graph_exec_) {
+    driver().GraphExecDestroy(graph_exec_);
+    graph_exec_ = nullptr;
+  }
+}
+
 void Solver::step_async() {
   ensure_context();
+  if (!(graph_enabled_ && !profiling_ && global_comm().nranks <= 1)) {
+    step_body();
+    return;
+  }
+  const DriverApi &d = driver();
+  if (!graph_exec_) {
+    // capture one step (nothing executes yet), instantiate, then replay below
+    const long long l0 = launches;
+    CUgraph graph = nullptr;
+    check(d.StreamBeginCapture(stream_, CU_STREAM_CAPTURE_MODE_RELAXED), "cuStreamBeginCapture");
+    try {
+      step_body();
+    } catch (...) {
+      d.StreamEndCapture(stream_, &graph);
+      if (graph)
+        d.GraphDestroy(graph);
+      throw;
+    }
+    check(d.StreamEndCapture(stream_, &graph), "cuStreamEndCapture");
+    graph_launches_ = launches - l0;
+    launches = l0;
+    CUresult r = d.GraphInstantiate(&graph_exec_, graph, 0);
+    d.GraphDestroy(graph);
+    check(r, "cuGraphInstantiate");
+  }
+  check(d.GraphLaunch(graph_exec_, stream_), "cuGraphLaunch");
+  launches += graph_launches_;
+}
+
+void Solver::step_body() {
   const int nd = cfg_.ndim, N = cfg_.N, V = cfg_.V;
   const int Nd = ipow(N, nd);
   const Comm &cm = global_comm();

@@ -122,6 +122,16 @@ private:
   // k_boundaries waits for it.  Inside a run the exchange is posted right after the edge
   // rows' k_update and overlaps the interior rows' update (and whatever the caller
   // enqueues between steps); halo_valid_ = false forces one at the start of a step.
+  // The kernel sequence of one step (all arguments are fixed for the life of the solver:
+  // dt, t and the step counter live in the device-side StepState).  On small grids, where a
+  // step is ten launches of a few microseconds each, step_async() captures it once into a
+  // CUDA graph and replays that (single GPU, profiling off; PYPDE_B200_GRAPH=0/1 overrides
+  // the size rule).
+  void step_body();
+  void drop_graph();
+  bool graph_enabled_ = false;
+  CUgraphExec graph_exec_ = nullptr;
+  long long graph_launches_ = 0;
   void post_halo_exchange();
   void update_cells(long cell0, long ncells);
   CUstream comm_stream_ = nullptr;

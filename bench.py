@@ -224,6 +224,10 @@ def main():
     ap.add_argument('--ref-size', type=int, default=128, help='grid of the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--analytic-wavespeed', action='store_true',
+                    help='OPT-IN experiment, never the default: analytic |v| + c through '
+                         'pypde_b200_set_wavespeed instead of the reference-defined finite-'
+                         'difference Jacobian eigen-solves (results differ at the 1e-8 level)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
 
@@ -250,6 +254,11 @@ def main():
         comm_init_from_torch()
 
     os.environ['PYPDE_B200_QUIET'] = '1'
+    if args.analytic_wavespeed:
+        from pypde_b200.systems import euler_wavespeed
+        from pypde_b200.utils import get_cdll
+        _ws = euler_wavespeed(2)
+        assert get_cdll().pypde_b200_set_wavespeed(_ws.pointer) == 0
     sampler = ClockSampler(local) if rank == 0 else None
     n = args.size
     K, W = args.steps, args.warmup
@@ -419,7 +428,12 @@ def main():
                        'flux': 'rusanov',
                        'l2': 'inputs larger than L2: w + traces = %.1f GB per step vs 126 MB L2'
                              % ((n + 2)**2 * (9 * 4 + 144) * 8 / 1e9),
-                       'parallelism': 'slab%d' % world},
+                       'parallelism': 'slab%d' % world,
+                       **({'wavespeed': 'analytic |v|+c via pypde_b200_set_wavespeed — OPT-IN '
+                                        'experiment, NOT the reference-defined path (its wave '
+                                        'speeds are spectral radii of finite-difference '
+                                        'Jacobians); not comparable with the default line'}
+                          if args.analytic_wavespeed else {})},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
             'cpu_baseline': cpu,
         }

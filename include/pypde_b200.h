@@ -108,6 +108,22 @@ int pypde_b200_host_spectral_radius_pair(const double *A0, const double *A1, int
 /* Same, for the Osher/Roe dissipation y = |A| x = Re(R |Lambda| R^-1 x). */
 int pypde_b200_host_abs_matrix_apply(const double *A, int n, const double *x, double *y);
 
+/* Stand-alone reconstruction with input and output resident in HBM (the device-pointer
+ * form of weno_solver, reference api.cpp:32-48): u_dev holds prod(nX) V doubles, ret_dev
+ * prod(nX_d - 2(N-1)) N^ndim V doubles; enqueued on `stream` (a CUstream / cudaStream_t,
+ * NULL = the legacy default stream) and complete on return. */
+int pypde_b200_weno_device(const void *u_dev, void *ret_dev, const int *nX, int ndim, int N, int V,
+                           void *stream);
+
+/* OPT-IN, not the reference's numbers: a device function
+ *   extern "C" __device__ double user_L(const double *q, const double *dq, int d)
+ * returning max |lambda| of dF_d/dQ + B_d at q.  While one is set, solvers created by
+ * pde_solver / pypde_b200_create use it in the CFL condition and the Rusanov flux instead of
+ * the finite-difference Jacobian + eigen-solve the reference defines (eigs/system.cpp:6-51);
+ * results then differ from the reference's at the level of its differencing noise (~1e-8
+ * relative in dt).  NULL restores the reference's definition.  The descriptor is copied. */
+int pypde_b200_set_wavespeed(const pypde_b200_devfn *L);
+
 /* JIT only (no GPU needed): specialise + link the kernels for a configuration
  * and return the sm_100a cubin size (and optionally the cubin).  Used by the
  * CPU test-suite and by build(). */

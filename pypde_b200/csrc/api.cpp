@@ -52,6 +52,8 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
       add(&fn[i]->kind, sizeof(int));
       add(fn[i]->image, fn[i]->bytes);
     }
+  if (c.useL)
+    k += wavespeed_key();
   for (const char *e : {"PYPDE_B200_EXTRA_DEFINES", "PYPDE_B200_FMA", "PYPDE_B200_EXACT_B",
                         "PYPDE_B200_EIG_QR_ONLY", "PYPDE_B200_WS_BLOCK", "PYPDE_B200_WS_MINBLOCKS",
                         "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES"}) {
@@ -80,6 +82,7 @@ KernelConfig make_config(int ndim, int N, int V, int FLUX, int STIFF, int second
   c.useB = B != nullptr;
   c.useS = S != nullptr;
   c.secondOrder = secondOrder != 0 && c.useF;
+  c.useL = c.useF && wavespeed_set();
   return c;
 }
 } // namespace
@@ -458,6 +461,23 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
   } catch (...) {
     set_error("pypde_b200: unknown error in pde_solver");
   }
+}
+
+int pypde_b200_set_wavespeed(const pypde_b200_devfn *L) {
+  API_TRY
+  set_wavespeed(L);
+  return 0;
+  API_CATCH(1)
+}
+
+int pypde_b200_weno_device(const void *u_dev, void *ret_dev, const int *nX, int ndim, int N, int V,
+                           void *stream) {
+  API_TRY
+  g_last_error.clear();
+  Solver::weno_device((CUdeviceptr)(uintptr_t)u_dev, (CUdeviceptr)(uintptr_t)ret_dev, nX, ndim, N,
+                      V, (CUstream)stream);
+  return 0;
+  API_CATCH(1)
 }
 
 void weno_solver(double *ret, double *_u, int *_nX, int ndim, int N, int V) {

@@ -163,7 +163,33 @@ std::string jl_log(JitLinkHandle h) {
 std::mutex g_cache_mutex;
 std::map<std::string, std::vector<char>> g_cache;
 
+// the opt-in wave-speed function (owned copy)
+std::mutex g_ws_mutex;
+std::string g_ws_image, g_ws_name;
+int g_ws_kind = -1;
+
 } // namespace
+
+void set_wavespeed(const pypde_b200_devfn *L) {
+  std::lock_guard<std::mutex> lk(g_ws_mutex);
+  if (!L || !L->image || L->bytes == 0) {
+    g_ws_image.clear();
+    g_ws_name.clear();
+    g_ws_kind = -1;
+    return;
+  }
+  g_ws_image.assign((const char *)L->image, L->bytes);
+  g_ws_name = L->name ? L->name : "user_L";
+  g_ws_kind = L->kind;
+}
+bool wavespeed_set() {
+  std::lock_guard<std::mutex> lk(g_ws_mutex);
+  return g_ws_kind >= 0;
+}
+std::string wavespeed_key() {
+  std::lock_guard<std::mutex> lk(g_ws_mutex);
+  return g_ws_kind < 0 ? std::string() : std::to_string(g_ws_kind) + ":" + g_ws_image;
+}
 
 void choose_block_shapes(KernelConfig &c) {
   const int Nd = ipow(c.N, c.ndim);
@@ -228,6 +254,7 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_USE_B", c.useB ? 1 : 0),
           kv("PDE_USE_S", c.useS ? 1 : 0),
           kv("PDE_SECOND_ORDER", c.secondOrder ? 1 : 0),
+          kv("PDE_USE_L", c.useL ? 1 : 0),
           kv("PDE_EXACT_B_PRODUCT", exact_b_product() ? 1 : 0),
           kv("PDE_EIG_QR_ONLY", getenv("PYPDE_B200_EIG_QR_ONLY") ? 1 : 0),
           kv("PDE_DG_CPB", c.dg_cpb),
@@ -266,6 +293,17 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
   const pypde_b200_devfn *fn[3] = {cfg.useF ? F : nullptr, cfg.useB ? B : nullptr,
                                    cfg.useS ? S : nullptr};
   const char *fn_names[3] = {"user_F", "user_B", "user_S"};
+  // the opt-in wave-speed function travels as a fourth image
+  std::string ws_image, ws_name;
+  int ws_kind = -1;
+  if (cfg.useL) {
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    ws_image = g_ws_image;
+    ws_name = g_ws_name;
+    ws_kind = g_ws_kind;
+    if (ws_kind < 0)
+      throw std::runtime_error("pypde_b200: configuration wants user_L but no wave-speed function is set");
+  }
 
   Hasher h;
   h.add(src);
@@ -282,6 +320,10 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
                                fn_names[i]);
     h.add(&fn[i]->kind, sizeof(int));
     h.add(fn[i]->image, fn[i]->bytes);
+  }
+  if (cfg.useL) {
+    h.add(&ws_kind, sizeof(int));
+    h.add(ws_image);
   }
   const std::string key = h.hex();
   {
@@ -348,9 +390,27 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
     if (rc != 0)
       fail(std::string("nvJitLinkAddData(") + fn_names[i] + ")", rc);
   }
+  if (cfg.useL) {
+    if (ws_kind == PYPDE_B200_LTOIR) {
+      rc = jl.AddData(lh, JITLINK_INPUT_LTOIR, ws_image.data(), ws_image.size(), ws_name.c_str());
+    } else if (ws_kind == PYPDE_B200_PTX) {
+      rc = jl.AddData(lh, JITLINK_INPUT_PTX, ws_image.data(), ws_image.size(), ws_name.c_str());
+    } else {
+      std::vector<char> ir;
+      try {
+        ir = nvrtc_to_ltoir(std::string(ws_image.c_str()), ws_name.c_str(), defs);
+      } catch (...) {
+        jl.Destroy(&lh);
+        throw;
+      }
+      rc = jl.AddData(lh, JITLINK_INPUT_LTOIR, ir.data(), ir.size(), ws_name.c_str());
+    }
+    if (rc != 0)
+      fail("nvJitLinkAddData(user_L)", rc);
+  }
   rc = jl.Complete(lh);
   if (rc != 0)
-    fail("nvJitLinkComplete (is a user_F/user_B/user_S symbol missing or mis-typed?)", rc);
+    fail("nvJitLinkComplete (is a user_F/user_B/user_S/user_L symbol missing or mis-typed?)", rc);
   size_t n = 0;
   rc = jl.GetLinkedCubinSize(lh, &n);
   if (rc != 0 || n == 0)

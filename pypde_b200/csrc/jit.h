@@ -14,6 +14,7 @@ namespace pypde {
 struct KernelConfig {
   int ndim = 1, N = 2, V = 1, flux = 0;
   bool stiff = false, useF = false, useB = false, useS = false, secondOrder = false;
+  bool useL = false; // opt-in user wave speed (pypde_b200_set_wavespeed) instead of the eigen-solves
   int dg_cpb = 1;    // cells per block in k_dg
   int faces_fpb = 1; // faces per block in k_faces
   int stiff_wpb = 4; // warps (cells) per block in k_dg_stiff
@@ -30,6 +31,14 @@ void choose_block_shapes(KernelConfig &c);
 // ($PYPDE_B200_CACHE, default /tmp/pypde_b200_cache-<uid>).
 std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F,
                               const pypde_b200_devfn *B, const pypde_b200_devfn *S);
+
+// The opt-in wave-speed function: a process-wide descriptor, copied by
+// pypde_b200_set_wavespeed; configurations built while it is set have useL = true and link
+//   extern "C" __device__ double user_L(const double *q, const double *dq, int d)
+// in place of the finite-difference Jacobian + eigen-solve of max_abs_eigs.
+void set_wavespeed(const pypde_b200_devfn *L);      // nullptr clears
+bool wavespeed_set();
+std::string wavespeed_key();                         // for cache keys (empty when unset)
 
 // The specialised CUDA source (tables + macros + kernels), for diagnostics and
 // for the offline nvcc build check.

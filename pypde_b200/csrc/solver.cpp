@@ -815,7 +815,8 @@ size_t Solver::read_stage(int which, double *out, size_t cap) {
 }
 
 // ---------------------------------------------------------------------------
-void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V) {
+void Solver::weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim, int N, int V,
+                         CUstream st) {
   if (ndim < 1 || ndim > 3)
     throw std::runtime_error("pypde_b200: weno_solver supports ndim 1..3");
   KernelConfig cfg;
@@ -828,20 +829,13 @@ void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, in
   Module mod(cfg, nullptr, nullptr, nullptr);
   int sms = 148;
   long shape[3] = {1, 1, 1};
-  size_t nin = V;
   for (int i = 0; i < ndim; i++) {
     shape[i] = nX[i];
-    nin *= nX[i];
     if (nX[i] < 2 * N - 1)
       throw std::runtime_error("pypde_b200: weno_solver needs at least 2N-1 cells per axis");
   }
-  CUstream st;
-  check(d.StreamCreate(&st, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
-  DeviceBuffer in, buf[2];
-  in.alloc(nin * sizeof(double));
-  check(d.MemcpyHtoDAsync(in.p, u, nin * sizeof(double), st), "cuMemcpyHtoDAsync");
-  CUdeviceptr cur = in.p;
-  size_t nout = nin;
+  DeviceBuffer buf[2];
+  CUdeviceptr cur = u;
   for (int dd = 0; dd < ndim; dd++) {
     long n1 = 1, n3 = 1;
     for (int i = 0; i < dd; i++)
@@ -852,10 +846,12 @@ void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, in
     long n34 = n3 * ipow(N, dd);
     int n1i = (int)n1;
     long total = n1 * (md - 2 * (N - 1)) * n34 * V;
-    nout = (size_t)total * N;
-    DeviceBuffer &o = buf[dd & 1];
-    o.alloc(nout * sizeof(double));
-    CUdeviceptr out = o.p;
+    CUdeviceptr out = ret; // the last sweep writes the result
+    if (dd < ndim - 1) {
+      DeviceBuffer &o = buf[dd & 1];
+      o.alloc((size_t)total * N * sizeof(double));
+      out = o.p;
+    }
     void *args[] = {&cur, &out, &n1i, &md, &n34};
     long blocks = (total + 255) / 256;
     if (blocks > sms * 16)
@@ -867,7 +863,30 @@ void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, in
     cur = out;
     shape[dd] -= 2 * (N - 1);
   }
-  check(d.MemcpyDtoHAsync(ret, cur, nout * sizeof(double), st), "cuMemcpyDtoHAsync");
+  // (the intermediates and the module are released on return)
+  check(d.StreamSynchronize(st), "cuStreamSynchronize");
+}
+
+void Solver::weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V) {
+  if (ndim < 1 || ndim > 3)
+    throw std::runtime_error("pypde_b200: weno_solver supports ndim 1..3");
+  ensure_context();
+  const DriverApi &d = driver();
+  size_t nin = V, nout = V;
+  for (int i = 0; i < ndim; i++) {
+    if (nX[i] < 2 * N - 1)
+      throw std::runtime_error("pypde_b200: weno_solver needs at least 2N-1 cells per axis");
+    nin *= nX[i];
+    nout *= (size_t)(nX[i] - 2 * (N - 1)) * N;
+  }
+  CUstream st;
+  check(d.StreamCreate(&st, CU_STREAM_NON_BLOCKING), "cuStreamCreate");
+  DeviceBuffer in, out;
+  in.alloc(nin * sizeof(double));
+  out.alloc(nout * sizeof(double));
+  check(d.MemcpyHtoDAsync(in.p, u, nin * sizeof(double), st), "cuMemcpyHtoDAsync");
+  weno_device(in.p, out.p, nX, ndim, N, V, st);
+  check(d.MemcpyDtoHAsync(ret, out.p, nout * sizeof(double), st), "cuMemcpyDtoHAsync");
   check(d.StreamSynchronize(st), "cuStreamSynchronize");
   d.StreamDestroy(st);
 }

@@ -89,6 +89,10 @@ public:
 
   // stand-alone reconstruction of an already padded array (api.cpp:32-48)
   static void weno_only(double *ret, const double *u, const int *nX, int ndim, int N, int V);
+  // the same with input and output resident in HBM (ret holds prod(nX_d - 2(N-1)) N^ndim V
+  // doubles), enqueued on `stream` and complete when this returns
+  static void weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim, int N, int V,
+                          CUstream stream);
 
   // per-kernel device times (CUDA events on the launching stream)
   void set_profiling(bool on);

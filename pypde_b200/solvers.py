@@ -42,10 +42,18 @@ def pde_solver(Q0,
                ndt=100,
                flux='rusanov',
                stiff=True,
-               nThreads=-1):
+               nThreads=-1,
+               wavespeed=None):
     """Solves dQ/dt + div F(Q, grad Q) + B(Q).grad Q = S(Q) with ADER-WENO on
     the GPU.  Same contract as reference pypde.pde_solver: returns an array of
     shape (ndt,) + Q0.shape; Q0 is advanced in place when it is C-contiguous.
+
+    `wavespeed` (not in the reference; opt-in) is a `CudaSource` defining
+    ``extern "C" __device__ double user_L(const double *q, const double *dq, int d)``,
+    the analytic max |lambda| of dF_d/dQ + B_d: it replaces the finite-difference
+    Jacobian + eigen-solve that the reference — and this library by default — uses
+    for the CFL condition and the Rusanov dissipation, so results differ from the
+    reference's at the level of its differencing noise (~1e-8 relative in dt).
     """
     nX = array(Q0.shape[:-1], dtype='int32')
     ndim = len(nX)
@@ -72,17 +80,54 @@ def pde_solver(Q0,
     if nThreads < 1:
         nThreads = cpu_count() - 1
 
-    solver(_F.ctypes if useF else None, _B.ctypes if useB else None,
-           _S.ctypes if useS else None, useF, useB, useS, c_ptr(ur), tf,
-           c_ptr(nX), ndim, c_ptr(dX), cfl, c_ptr(boundaryTypes), stiff,
-           FLUXES[flux], order, V, ndt, secondOrder, c_ptr(ret), nThreads)
-    check_error('pde_solver')
+    lib = get_cdll()
+    if wavespeed is not None:
+        if not isinstance(wavespeed, DeviceFunction):
+            raise TypeError('pypde_b200: wavespeed must be a CudaSource / DeviceFunction '
+                            'defining user_L')
+        if lib.pypde_b200_set_wavespeed(wavespeed.ctypes) != 0:
+            check_error('pypde_b200_set_wavespeed')
+    try:
+        solver(_F.ctypes if useF else None, _B.ctypes if useB else None,
+               _S.ctypes if useS else None, useF, useB, useS, c_ptr(ur), tf,
+               c_ptr(nX), ndim, c_ptr(dX), cfl, c_ptr(boundaryTypes), stiff,
+               FLUXES[flux], order, V, ndt, secondOrder, c_ptr(ret), nThreads)
+        check_error('pde_solver')
+    finally:
+        if wavespeed is not None:
+            lib.pypde_b200_set_wavespeed(None)
 
     return ret.reshape((ndt, ) + Q0.shape)
 
 
+def _weno_solver_torch(u, order):
+    """u: a float64 CUDA tensor; returns a CUDA tensor (nothing crosses PCIe)."""
+    import torch
+    from ctypes import c_void_p
+    u = u.contiguous()
+    if u.dtype != torch.float64:
+        raise TypeError('pypde_b200.weno_solver: CUDA tensors must be float64')
+    nX = array(u.shape[:-1], dtype=int32)
+    ndim, V = len(nX), u.shape[-1]
+    nXret = nX - 2 * (order - 1)
+    ret = torch.empty(tuple(int(x) for x in nXret) + (order, ) * ndim + (V, ),
+                      dtype=torch.float64, device=u.device)
+    lib = get_cdll()
+    lib.pypde_b200_weno_device.argtypes = [c_void_p, c_void_p, POINTER(c_int), c_int, c_int, c_int,
+                                           c_void_p]
+    with torch.cuda.device(u.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if lib.pypde_b200_weno_device(u.data_ptr(), ret.data_ptr(), c_ptr(nX), ndim, order, V,
+                                      stream) != 0:
+            check_error('weno_solver')
+    return ret
+
+
 def weno_solver(u, order=2):
-    """Stand-alone WENO reconstruction (reference solvers.py:217-244)."""
+    """Stand-alone WENO reconstruction (reference solvers.py:217-244).  A float64 CUDA
+    torch tensor is reconstructed in place in HBM and a CUDA tensor is returned."""
+    if getattr(u, 'is_cuda', False):
+        return _weno_solver_torch(u, order)
     u = ascontiguousarray(u, dtype='float64')
     nX = array(u.shape[:-1], dtype=int32)
     ndim = len(nX)

@@ -54,3 +54,18 @@ def cuda_sources(system, ndim, defines=None):
 
     return (one('F') if hasF else None, one('B') if hasB else None,
             one('S') if hasS else None, vfun(ndim))
+
+
+def euler_wavespeed(ndim):
+    """OPT-IN analytic wave speed |v_d| + c of the Euler system above, for
+    `pde_solver(..., wavespeed=...)` / `pypde_b200_set_wavespeed` (not the reference's
+    finite-difference definition: see include/pypde_b200.h)."""
+    return CudaSource(
+        'extern "C" __device__ double user_L(const double *Q, const double *dQ, int d) {\n'
+        '  const double g = 1.4;\n'
+        '  const double r = Q[0], ir = 1. / r;\n'
+        '  double vv = 0.;\n'
+        '  for (int i = 0; i < %d; i++) { const double v = Q[2 + i] * ir; vv += v * v; }\n'
+        '  const double p = (g - 1.) * (Q[1] - 0.5 * r * vv);\n'
+        '  return fabs(Q[2 + d] * ir) + sqrt(g * p * ir);\n'
+        '}\n' % ndim, 'euler_%dd_L' % ndim)

@@ -88,6 +88,36 @@ def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
         assert 'UTMALDG' in sass and 'SYNCS' in sass      # TMA bulk-tensor load + mbarrier
 
 
+def test_jit_links_the_opt_in_wavespeed_function():
+    """pypde_b200_set_wavespeed: configurations built while a user_L is set link it in place
+    of the eigen-solves (no cold QR code left in the fused face kernel); clearing restores
+    the reference's definition."""
+    from pypde_b200.systems import euler_wavespeed
+    lib = get_cdll()
+    F, B, S, V = cuda_sources('euler', 2)
+    L = euler_wavespeed(2)
+
+    def build():
+        n = ctypes.c_size_t()
+        buf = ctypes.create_string_buffer(8 << 20)
+        rc = lib.pypde_b200_compile(F.pointer, None, None, 2, 3, V, 0, 0, 0, ctypes.byref(n), buf,
+                                    ctypes.c_size_t(8 << 20))
+        assert rc == 0, last_error()
+        path = '/tmp/pypde_b200_test_ws.cubin'
+        open(path, 'wb').write(buf.raw[:n.value])
+        sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', 'k_faces_fused',
+                                        path]).decode()
+        return sass.count('\n')
+
+    assert lib.pypde_b200_set_wavespeed(L.pointer) == 0
+    try:
+        with_l = build()
+    finally:
+        assert lib.pypde_b200_set_wavespeed(None) == 0
+    without = build()
+    assert with_l < without / 4          # the eigen-solver is gone from the kernel
+
+
 def test_jit_reports_user_function_errors():
     lib = get_cdll()
     bad = CudaSource('extern "C" __device__ void user_F(double* o, const double* q, '

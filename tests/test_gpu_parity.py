@@ -115,6 +115,32 @@ def test_kernel_variants_agree_bit_for_bit(name, env):
     assert np.array_equal(outs[0], outs[1])
 
 
+def test_weno_solver_on_a_cuda_tensor():
+    """weno_solver(torch CUDA tensor) -> CUDA tensor, bit-identical to the host-buffer call."""
+    import torch
+    for shape, N in [((40, 5), 3), ((17, 13, 4), 3), ((9, 10, 11, 2), 2)]:
+        u = cases.weno_random(shape, seed=sum(shape))
+        w_host = pypde_b200.weno_solver(u, N)
+        w_dev = pypde_b200.weno_solver(torch.from_numpy(u).cuda(), N)
+        assert w_dev.is_cuda and tuple(w_dev.shape) == w_host.shape
+        assert np.array_equal(w_dev.cpu().numpy(), w_host)
+
+
+def test_opt_in_analytic_wavespeed():
+    """pde_solver(..., wavespeed=user_L): the analytic |v| + c replaces the finite-difference
+    Jacobian eigen-solves.  Opt-in because it is NOT the reference's definition: the result
+    agrees with the default path to the level of the reference's differencing noise, not to
+    rounding."""
+    from pypde_b200.systems import euler_wavespeed
+    c = cases.solver_cases()['euler2d_smooth_N3']
+    base, _ = run_gpu(c)
+    fast, _ = run_gpu(c, wavespeed=euler_wavespeed(2))
+    again, _ = run_gpu(c)
+    assert np.array_equal(base, again)           # the hook does not outlive its call
+    err = rel_linf(fast[0], base[0])
+    assert 0. < err < 1e-6, err
+
+
 def test_ret_row_semantics():
     """iterator.cpp:136-139,150: at most one row per step; unreached rows stay
     zero; the last row is the final state."""

@@ -64,6 +64,7 @@ def algorithmic_model(n):
         'k_dg': cw * (Nd * V + 2 * NDIM * NP * V) * D,
         'k_dg_n': cw * (Nd * V + 2 * NDIM * NP * V) * D,             # w in, face traces out
         'k_faces_fused': n * (n + 1) * (2 * NP * V + V) * D,         # per direction: traces in, flux out
+        'k_faces_side': n * (n + 1) * (2 * NP * V + V) * D,          # the same, two threads per face
         'k_wavespeeds': cw * 2 * NDIM * NP * (V + 1) * D,            # traces in, lambda out
         'k_faces': n * (n + 1) * (2 * NP * (V + 1) + V) * D,         # per direction
         'k_update': cells * V * D * 2 + NDIM * n * (n + 1) * V * D,
@@ -340,7 +341,8 @@ def main():
                  'node), not HBM bound; fp64 figures below' % dom),
         'fp64': {'achieved_tflops': (f_faces * n * n / (dom_ms * 1e-3) / 1e12)
                  if dom == 'k_wavespeeds' else
-                 ((f_faces / NDIM) * n * n / (dom_ms * 1e-3) / 1e12 if dom == 'k_faces_fused'
+                 ((f_faces / NDIM) * n * n / (dom_ms * 1e-3) / 1e12
+                  if dom in ('k_faces_fused', 'k_faces_side')
                   else None),
                  'peak_tflops': fp64_peak, 'peak_source': 'measured DFMA micro-kernel (k_fp64_peak)'},
         'kernels_ms_per_step': {k_: kt[k_][0] / P for k_ in kt},

@@ -56,7 +56,10 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
     k += wavespeed_key();
   for (const char *e : {"PYPDE_B200_EXTRA_DEFINES", "PYPDE_B200_FMA", "PYPDE_B200_EXACT_B",
                         "PYPDE_B200_EIG_QR_ONLY", "PYPDE_B200_WS_BLOCK", "PYPDE_B200_WS_MINBLOCKS",
-                        "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES"}) {
+                        "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES",
+                        "PYPDE_B200_FACES_SIDE", "PYPDE_B200_DG_NODE", "PYPDE_B200_WENO_FUSED",
+                        "PYPDE_B200_GRAPH", "PYPDE_B200_FF_BLOCK", "PYPDE_B200_FF_MINBLOCKS",
+                        "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS"}) {
     const char *v = getenv(e);
     k += v ? v : "-";
     k += '|';

@@ -233,6 +233,10 @@ void choose_block_shapes(KernelConfig &c) {
     c.ff_block = atoi(e);
   if (const char *e = getenv("PYPDE_B200_FF_MINBLOCKS"))
     c.ff_minblocks = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_FS_BLOCK"))
+    c.fs_block = atoi(e);
+  if (const char *e = getenv("PYPDE_B200_FS_MINBLOCKS"))
+    c.fs_minblocks = atoi(e);
   if (const char *e = getenv("PYPDE_B200_DG_CPB"))
     c.dg_cpb = atoi(e);
   if (const char *e = getenv("PYPDE_B200_FACES_FPB"))
@@ -263,7 +267,9 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_WS_BLOCK", c.ws_block),
           kv("PDE_WS_MINBLOCKS", c.ws_minblocks),
           kv("PDE_FF_BLOCK", c.ff_block),
-          kv("PDE_FF_MINBLOCKS", c.ff_minblocks)};
+          kv("PDE_FF_MINBLOCKS", c.ff_minblocks),
+          kv("PDE_FS_BLOCK", c.fs_block),
+          kv("PDE_FS_MINBLOCKS", c.fs_minblocks)};
   // tuning experiments: PYPDE_B200_EXTRA_DEFINES="PDE_X=1;PDE_Y=0"
   if (const char *e = getenv("PYPDE_B200_EXTRA_DEFINES")) {
     std::string all(e);

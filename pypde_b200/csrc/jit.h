@@ -20,6 +20,7 @@ struct KernelConfig {
   int stiff_wpb = 4; // warps (cells) per block in k_dg_stiff
   int ws_block = 512, ws_minblocks = 1; // k_wavespeeds launch bounds (measured best: C5 14.8 ms vs 22.1 at 256 x 2)
   int ff_block = 256, ff_minblocks = 2; // k_faces_fused launch bounds (measured best at C2)
+  int fs_block = 256, fs_minblocks = 2; // k_faces_side (experiment)
 };
 
 // Chooses the block shapes for a configuration (threads <= 256 where possible,

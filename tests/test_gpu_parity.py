@@ -95,14 +95,17 @@ def test_solver_golden(golden, name):
     ('euler3d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('burgers2d_N2', 'PYPDE_B200_DG_NODE'),
     ('euler2d_explosion_N3', 'PYPDE_B200_FUSED_FACES'), ('sod_N2', 'PYPDE_B200_FUSED_FACES'),
     ('euler3d_smooth_N2', 'PYPDE_B200_FUSED_FACES'),
+    ('euler2d_explosion_N3', 'PYPDE_B200_FACES_SIDE'), ('sod_N2', 'PYPDE_B200_FACES_SIDE'),
+    ('euler3d_smooth_N2', 'PYPDE_B200_FACES_SIDE'), ('burgers2d_N2', 'PYPDE_B200_FACES_SIDE'),
+    ('reactive1d_smooth_N3_stiff', 'PYPDE_B200_FACES_SIDE'),
     ('euler2d_explosion_N3', 'PYPDE_B200_WENO_FUSED'), ('euler2d_smooth_N2', 'PYPDE_B200_WENO_FUSED'),
     ('burgers2d_N2', 'PYPDE_B200_WENO_FUSED'), ('advect_nc_2d_N2', 'PYPDE_B200_WENO_FUSED'),
     ('euler2d_strip_N2', 'PYPDE_B200_WENO_FUSED'), ('gpr2d_N2_stiff', 'PYPDE_B200_WENO_FUSED')])
 def test_kernel_variants_agree_bit_for_bit(name, env):
-    """The node-thread predictor (k_dg_n), the fused Rusanov face kernel
-    (k_faces_fused) and the TMA-fed two-sweep WENO tile kernel (k_weno2d) run every
-    sum in the order of the general kernels they replace (k_dg; k_wavespeeds +
-    k_faces; k_weno_sweep x 2): same bits, whole runs."""
+    """The node-thread predictor (k_dg_n), the fused Rusanov face kernels (k_faces_side:
+    two threads per face; k_faces_fused: one) and the TMA-fed two-sweep WENO tile kernel
+    (k_weno2d) run every sum in the order of the general kernels they replace (k_dg;
+    k_wavespeeds + k_faces; k_weno_sweep x 2): same bits, whole runs."""
     c = cases.solver_cases()[name]
     outs = []
     for val in ('1', '0'):

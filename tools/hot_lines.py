@@ -3,6 +3,11 @@ page, SASS) to lines of the specialised CUDA source, using the line table of
 the identical cubin built locally (`nvdisasm -g`).
 
     python tools/hot_lines.py <report.ncu-rep> <cubin> <kernel> [top]
+
+The cubin must be the one the report was taken from (tools/sass_stats.py: build_cubin
+rebuilds it here — the JIT is deterministic).  HOT_LINES_CFG=ndim,N,V,useF,useB,useS,secondOrder
+selects the specialised source whose lines are printed (default 2,3,4,1,0,0,0 = BASELINE
+configs[1]).
 """
 import collections
 import csv

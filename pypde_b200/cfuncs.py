@@ -45,7 +45,11 @@ class _DevFn(Structure):
 class DeviceFunction:
     """A device function image + the C descriptor that points at it."""
 
-    def __init__(self, image, kind, name):
+    def __init__(self, image, kind, name, second_order=None):
+        # second_order (F only): True if the function reads dQ — the reference decides this
+        # by F's arity (solvers.py:196), which a compiled image does not show.  None =
+        # not stated: pde_solver then needs its secondOrder= argument.
+        self.second_order = second_order
         if isinstance(image, str):
             image = image.encode()
         if kind in (PTX, CUDA_SOURCE) and not image.endswith(b'\0'):
@@ -71,8 +75,8 @@ class DeviceFunction:
 class CudaSource(DeviceFunction):
     """CUDA C++ text defining `extern "C" __device__ void user_F/B/S(...)`."""
 
-    def __init__(self, source, name='user_function'):
-        super().__init__(source, CUDA_SOURCE, name)
+    def __init__(self, source, name='user_function', second_order=None):
+        super().__init__(source, CUDA_SOURCE, name, second_order)
 
 
 class _offline_device:

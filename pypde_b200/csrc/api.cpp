@@ -11,6 +11,8 @@
 #include <mutex>
 #include <string.h>
 #include <string>
+#include <thread>
+#include <vector>
 
 using namespace pypde;
 
@@ -59,7 +61,9 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
                         "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES",
                         "PYPDE_B200_FACES_SIDE", "PYPDE_B200_DG_NODE", "PYPDE_B200_WENO_FUSED",
                         "PYPDE_B200_GRAPH", "PYPDE_B200_FF_BLOCK", "PYPDE_B200_FF_MINBLOCKS",
-                        "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS"}) {
+                        "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS", "PYPDE_B200_STIFF_V1",
+                        "PYPDE_B200_STIFF_KS", "PYPDE_B200_STIFF_WPB", "PYPDE_B200_STIFF_MINBLOCKS",
+                        "PYPDE_B200_STIFF_STATS", "PYPDE_B200_WENO3D", "PYPDE_B200_EIG_HESS"}) {
     const char *v = getenv(e);
     k += v ? v : "-";
     k += '|';
@@ -370,6 +374,27 @@ int pypde_b200_comm_finalize(void) {
   API_CATCH(1)
 }
 
+// dst <- src (n doubles, not overlapping), split over a few threads when large
+static void host_copy(double *dst, const double *src, size_t n) {
+  const size_t big = (size_t)4 << 20; // doubles per thread below which threads do not pay
+  size_t nthreads = n / big;
+  if (nthreads > 4)
+    nthreads = 4;
+  if (nthreads < 2) {
+    memcpy(dst, src, n * sizeof(double));
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t chunk = (n + nthreads - 1) / nthreads;
+  for (size_t i = 0; i < nthreads; i++) {
+    const size_t a = i * chunk, b = a + chunk < n ? a + chunk : n;
+    if (a < b)
+      pool.emplace_back([=] { memcpy(dst + a, src + a, (b - a) * sizeof(double)); });
+  }
+  for (std::thread &t : pool)
+    t.join();
+}
+
 // ---------------------------------------------------------------------------
 // The reference's entry points (src/api.h:4-13)
 // ---------------------------------------------------------------------------
@@ -455,10 +480,12 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     }
     fflush(stdout);
     solver.drain_snapshots();
-    // iterator.cpp:150 and the in-place update of _u (api.cpp:18, iterator.cpp:129)
+    // iterator.cpp:150 and the in-place update of _u (api.cpp:18, iterator.cpp:129): the
+    // final state crosses PCIe once; its second destination is a host copy (threaded when
+    // large — eight ranks on one host share the PCIe uplinks, not the memory channels)
     solver.get_state(_u);
     if (ndt >= 1)
-      solver.get_state(_ret + (size_t)(ndt - 1) * n);
+      host_copy(_ret + (size_t)(ndt - 1) * n, _u, n);
   } catch (const std::exception &e) {
     set_error(e.what());
   } catch (...) {

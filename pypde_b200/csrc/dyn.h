@@ -107,7 +107,7 @@ struct NcclApi {
   int (*AllReduce)(const void *, void *, size_t, int /*dtype*/, int /*op*/, NcclComm, CUstream);
   const char *(*GetErrorString)(int);
 };
-enum { NCCL_FLOAT64 = 8, NCCL_UINT64 = 5, NCCL_MAX = 2 };
+enum { NCCL_FLOAT64 = 8, NCCL_UINT64 = 5, NCCL_INT32 = 2, NCCL_MAX = 2 };
 
 // Each throws std::runtime_error with a clear message if the library or a
 // symbol is missing.

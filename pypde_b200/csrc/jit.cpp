@@ -51,17 +51,33 @@ struct Hasher {
   }
 };
 
+// On-disk cubin cache.  The cubins in it are loaded as trusted GPU code, so the directory
+// must be this user's alone: default $XDG_CACHE_HOME/pypde_b200 or ~/.cache/pypde_b200
+// (PYPDE_B200_CACHE overrides), created 0700, and refused — the disk cache is then simply
+// not used — unless lstat shows a real directory (no symlink) owned by getuid() that
+// neither group nor others can write or read.  Returns "" when there is no usable one.
 std::string cache_dir() {
-  const char *e = getenv("PYPDE_B200_CACHE");
   std::string d;
+  const char *e = getenv("PYPDE_B200_CACHE");
   if (e && *e)
     d = e;
   else {
-    char buf[64];
-    snprintf(buf, sizeof buf, "/tmp/pypde_b200_cache-%d", (int)getuid());
-    d = buf;
+    const char *x = getenv("XDG_CACHE_HOME");
+    const char *h = getenv("HOME");
+    if (x && *x == '/')
+      d = std::string(x);
+    else if (h && *h == '/') {
+      d = std::string(h) + "/.cache";
+      mkdir(d.c_str(), 0700); // (may exist with the user's own mode: only our leaf is checked)
+    } else
+      return std::string();
+    d += "/pypde_b200";
   }
   mkdir(d.c_str(), 0700);
+  struct stat st;
+  if (lstat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() ||
+      (st.st_mode & 077) != 0)
+    return std::string();
   return d;
 }
 
@@ -218,12 +234,44 @@ void choose_block_shapes(KernelConfig &c) {
   while (fpb > 1 && (size_t)fpb * NP * sm_pt > 48 * 1024)
     fpb--;
   c.faces_fpb = fpb;
-  // k_dg_stiff: one warp per cell, (6+ndim) n doubles of shared memory per warp
-  const size_t sm_warp = (size_t)(6 + c.ndim) * NT * c.V * 8;
-  int wpb = 4;
-  while (wpb > 1 && wpb * sm_warp > 96 * 1024)
-    wpb--;
-  c.stiff_wpb = wpb;
+  // k_dg_stiff: one warp per cell.  Shared memory per warp (kernels.cuh: NK_SMEM2) =
+  // (5+ndim) n doubles of evaluation state + KS resident Krylov vectors of n doubles +
+  // KS Hessenberg columns + 4 x 41 doubles of Givens / least-squares data.  KS is what
+  // fits with 16 warps per SM resident (the register file allows no more at 128
+  // registers per thread), at least 2 and at most 12 (a Newton step of the BASELINE
+  // configurations needs 3-8 inner iterations).
+  {
+    const size_t n = (size_t)NT * c.V;
+    if (const char *e = getenv("PYPDE_B200_STIFF_V1"))
+      c.stiff_v1 = *e == '1';
+    if (const char *e = getenv("PYPDE_B200_STIFF_STATS"))
+      c.stiff_stats = *e == '1';
+    const long budget = 227 * 1024 / 16 / 8 - 4 * 41 - (long)(5 + c.ndim) * (long)n; // doubles
+    int ks = 2;
+    while (ks < 12 && (long)(ks + 1) * (long)n + (long)(ks + 1) * (ks + 2) <= budget)
+      ks++;
+    if (const char *e = getenv("PYPDE_B200_STIFF_KS"))
+      ks = atoi(e) < 1 ? 1 : (atoi(e) > 40 ? 40 : atoi(e));
+    c.stiff_ks = ks;
+    auto sm_warp = [&]() {
+      return c.stiff_v1 ? (size_t)(6 + c.ndim) * n * 8
+                        : ((size_t)(5 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 1) +
+                           4 * 41) * 8;
+    };
+    int wpb = 4;
+    if (const char *e = getenv("PYPDE_B200_STIFF_WPB"))
+      wpb = atoi(e) < 1 ? 1 : atoi(e);
+    while (c.stiff_ks > 1 && sm_warp() > 220 * 1024)
+      c.stiff_ks--;
+    while (wpb > 1 && wpb * sm_warp() > (c.stiff_v1 ? 96 : 110) * 1024)
+      wpb--;
+    c.stiff_wpb = wpb;
+    // 4 blocks of 4 warps per SM <-> 128 registers per thread: no spills for V <= 8 (reactive
+    // Euler: 158 uncapped); larger systems (GPR, V = 17: 254 uncapped) keep the full budget
+    c.stiff_minblocks = (c.V <= 8 && wpb == 4 && !c.stiff_v1) ? 4 : 1;
+    if (const char *e = getenv("PYPDE_B200_STIFF_MINBLOCKS"))
+      c.stiff_minblocks = atoi(e);
+  }
   // tuning overrides (experiments)
   if (const char *e = getenv("PYPDE_B200_WS_BLOCK"))
     c.ws_block = atoi(e);
@@ -264,6 +312,10 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb),
           kv("PDE_STIFF_WPB", c.stiff_wpb),
+          kv("PDE_STIFF_KS", c.stiff_ks),
+          kv("PDE_STIFF_MINBLOCKS", c.stiff_minblocks),
+          kv("PDE_STIFF_V1", c.stiff_v1 ? 1 : 0),
+          kv("PDE_STIFF_STATS", c.stiff_stats ? 1 : 0),
           kv("PDE_WS_BLOCK", c.ws_block),
           kv("PDE_WS_MINBLOCKS", c.ws_minblocks),
           kv("PDE_FF_BLOCK", c.ff_block),
@@ -316,6 +368,16 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
   for (const std::string &d : defs)
     h.add(d);
   h.add(fma_enabled() ? "fma1" : "fma0");
+  {
+    // a toolkit upgrade must not reuse cubins of the old compiler / linker
+    int v[4] = {0, 0, 0, 0};
+    unsigned lv[2] = {0, 0};
+    nvrtc().Version(&v[0], &v[1]);
+    jitlink().Version(&lv[0], &lv[1]);
+    v[2] = (int)lv[0];
+    v[3] = (int)lv[1];
+    h.add(v, sizeof v);
+  }
   for (int i = 0; i < 3; i++) {
     if (!fn[i]) {
       h.add("-");
@@ -338,8 +400,9 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
     if (it != g_cache.end())
       return it->second;
   }
-  const bool use_disk = !(getenv("PYPDE_B200_NO_DISK_CACHE"));
-  const std::string path = cache_dir() + "/" + key + ".cubin";
+  const std::string dir = getenv("PYPDE_B200_NO_DISK_CACHE") ? std::string() : cache_dir();
+  const bool use_disk = !dir.empty();
+  const std::string path = dir + "/" + key + ".cubin";
   std::vector<char> cubin;
   if (use_disk && read_file(path, cubin)) {
     std::lock_guard<std::mutex> lk(g_cache_mutex);

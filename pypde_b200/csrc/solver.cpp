@@ -36,6 +36,16 @@ bool weno2d_tile(const KernelConfig &c, int *ti_out, int *tj_out) {
   return true;
 }
 
+// kernels.cuh: DGN_OK — where k_dg_n is compiled
+bool dgn_ok(const KernelConfig &c) {
+  const int Nd = ipow(c.N, c.ndim);
+  if (c.useB || c.secondOrder || c.N < 2 || Nd > 32)
+    return false;
+  const int cpw = 32 / Nd, fs = c.ndim * c.N * c.V * Nd;
+  const int sm_cell = fs + ((Nd % 16) + 16 - (fs % 16)) % 16;
+  return (long)cpw * sm_cell * 8 <= 48 * 1024;
+}
+
 void check(CUresult r, const char *what) {
   if (r == CUDA_SUCCESS)
     return;
@@ -113,8 +123,7 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     get(k_dg_stiff, "k_dg_stiff");
   if (cfg.useF && cfg.flux == 0)
     get(k_faces_fused, "k_faces_fused");
-  // kernels.cuh: DGN_OK
-  if (!cfg.useB && !cfg.secondOrder && cfg.N >= 2 && ipow(cfg.N, cfg.ndim) <= 32)
+  if (dgn_ok(cfg))
     get(k_dg_n, "k_dg_n");
   if (weno2d_tile(cfg, nullptr, nullptr))
     get(k_weno2d, "k_weno2d");
@@ -164,6 +173,12 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     if (const char *e = getenv("PYPDE_B200_GRAPH"))
       graph_enabled_ = *e != '0';
   }
+  // PYPDE_B200_PREBUILD=1 (build box, no GPU): JIT this configuration's cubin into the
+  // on-disk cache before the device is asked for, so that a later run on a GPU box that
+  // shares the cache directory ($PYPDE_B200_CACHE) starts without compiling
+  if (const char *e = getenv("PYPDE_B200_PREBUILD"))
+    if (*e == '1')
+      build_cubin(cfg_, F, B, S);
   ensure_context();
   const DriverApi &d = driver();
   CUdevice dev;
@@ -273,20 +288,28 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   own_stream_ = true;
 
   if (cfg_.stiff) {
-    // one warp per cell; global workspace per warp (kernels.cuh: NK_WORK)
+    // one warp per cell, cells drawn from a device-side queue; global workspace per warp
+    // (kernels.cuh: NK_WORK) for the Krylov vectors beyond the shared-memory resident ones
     const size_t n = (size_t)N * Nd * V;
     const size_t nk_work = 41 * n + 10 * n + 42 * 41 + 6 * 41;
     stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
-    const size_t smem_warp = (6 + nd) * n * D;
+    const size_t smem_warp =
+        cfg_.stiff_v1 ? (6 + nd) * n * D
+                      : ((5 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 1) + 4 * 41) * D;
     if (smem_warp > 220 * 1024)
       throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
+    stiff_smem_ = stiff_wpb_ * smem_warp;
     long blocks = (ncellw_ + stiff_wpb_ - 1) / stiff_wpb_;
     long cap = (long)sms_ * 8;
     stiff_blocks_ = blocks < cap ? blocks : cap;
-    stiff_work_.alloc((size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D);
-    if (stiff_wpb_ * smem_warp > 48 * 1024)
+    // (+ 64 bytes: the iteration counters of PDE_STIFF_STATS)
+    stiff_work_.alloc((size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D + 64);
+    check(d.MemsetD8Async(stiff_work_.p + (size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D, 0, 64,
+                          stream_),
+          "cuMemsetD8Async(stiff stats)");
+    if (stiff_smem_ > 48 * 1024)
       check(d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                               (int)(stiff_wpb_ * smem_warp)),
+                               (int)stiff_smem_),
             "cuFuncSetAttribute(k_dg_stiff smem)");
   }
   // dynamic shared memory opt-in
@@ -705,9 +728,9 @@ void Solver::step_body() {
     launch(mod_->k_dt, 1, 1, 0, args, "k_dt");
   }
   if (cfg_.stiff) {
-    const size_t smem = (size_t)stiff_wpb_ * (6 + nd) * N * Nd * V * sizeof(double);
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p, &stiff_work_.p};
-    launch(mod_->k_dg_stiff, (unsigned)stiff_blocks_, 32 * stiff_wpb_, smem, args, "k_dg_stiff");
+    launch(mod_->k_dg_stiff, (unsigned)stiff_blocks_, 32 * stiff_wpb_, stiff_smem_, args,
+           "k_dg_stiff");
   } else if (node_dg_ && mod_->k_dg_n) {
     // one thread per spatial node, 32 / N^ndim cells per one-warp block
     const int cpw = 32 / Nd;
@@ -771,6 +794,17 @@ void Solver::step_body() {
     if (cm.nranks > 1)
       post_halo_exchange();
   }
+  if (cm.nranks > 1) {
+    // The NaN stop of iterator.cpp:141-145 must be the same decision on every rank:
+    // k_update raises nan_flag from this rank's own cells only, and a rank that left the
+    // time loop alone would leave the others waiting in the next dt reduction / halo
+    // exchange for ever.  One 4-byte max-all-reduce per step (~10 us against milliseconds).
+    const NcclApi &nc = nccl();
+    CUdeviceptr nf = state_.p + offsetof(StepState, nan_flag);
+    int r = nc.AllReduce((const void *)nf, (void *)nf, 1, NCCL_INT32, NCCL_MAX, cm.comm, stream_);
+    if (r != 0)
+      throw std::runtime_error(std::string("pypde_b200: ncclAllReduce(nan): ") + nc.GetErrorString(r));
+  }
   {
     void *args[] = {&state_.p};
     launch(mod_->k_advance, 1, 1, 0, args, "k_advance");
@@ -809,6 +843,17 @@ size_t Solver::read_stage(int which, double *out, size_t cap) {
   case 7:
     b = &ws_;
     break;
+  case 8: { // k_dg_stiff iteration counters (PYPDE_B200_STIFF_STATS=1): 4 x u64 as raw doubles
+    if (!stiff_work_.p)
+      throw std::runtime_error("pypde_b200: not a stiff solver");
+    const DriverApi &dd = driver();
+    if (out && cap >= 4) {
+      check(dd.MemcpyDtoHAsync(out, stiff_work_.p + stiff_work_.bytes - 64, 32, stream_),
+            "cuMemcpyDtoHAsync(stiff stats)");
+      check(dd.StreamSynchronize(stream_), "cuStreamSynchronize");
+    }
+    return 4;
+  }
   default:
     if (which >= 4 && which < 4 + cfg_.ndim)
       b = &flx_[which - 4];
@@ -835,6 +880,9 @@ void Solver::weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim
   cfg.N = N;
   cfg.V = V;
   choose_block_shapes(cfg);
+  if (const char *e = getenv("PYPDE_B200_PREBUILD"))
+    if (*e == '1')
+      build_cubin(cfg, nullptr, nullptr, nullptr);
   ensure_context();
   const DriverApi &d = driver();
   Module mod(cfg, nullptr, nullptr, nullptr);

@@ -24,6 +24,7 @@ struct StepState {
   long long count;
   int nan_flag;
   int pad;
+  unsigned long long stiff_next;
 };
 struct FluxPtrs {
   CUdeviceptr f[3];
@@ -161,6 +162,7 @@ private:
   int weno2d_ti_ = 0, weno2d_tj_ = 0;
   CUtensorMap ub_map_;
   int stiff_wpb_ = 4;
+  size_t stiff_smem_ = 0; // dynamic shared memory of k_dg_stiff per block
   long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,
       flx_[3], state_;

@@ -52,7 +52,8 @@ def _check(rc, what):
         raise RuntimeError('%s failed: %s' % (what, last_error()))
 
 
-STAGES = {'ub': 0, 'w': 1, 'traces': 2, 'centers': 3, 'flux0': 4, 'flux1': 5, 'flux2': 6, 'wavespeeds': 7}
+STAGES = {'ub': 0, 'w': 1, 'traces': 2, 'centers': 3, 'flux0': 4, 'flux1': 5, 'flux2': 6, 'wavespeeds': 7,
+          'stiff_stats': 8}
 
 
 class Solver:
@@ -63,7 +64,7 @@ class Solver:
     """
 
     def __init__(self, shape, L, F=None, B=None, S=None, boundaryTypes='transitive', cfl=0.9,
-                 order=2, flux='rusanov', stiff=False, dX=None):
+                 order=2, flux='rusanov', stiff=False, dX=None, secondOrder=None):
         self.lib = _lib()
         self.shape = tuple(int(s) for s in shape)
         nX = np.array(self.shape[:-1], dtype='int32')
@@ -82,7 +83,7 @@ class Solver:
                                           self.dX.ctypes.data_as(POINTER(c_double)), cfl,
                                           bt.ctypes.data_as(POINTER(c_int)), int(stiff),
                                           FLUXES[flux], order, self.V,
-                                          int(_is_second_order(self._fns[0]))),
+                                          int(_is_second_order(self._fns[0], secondOrder))),
                'pypde_b200_create')
         self.ncell = int(nX.prod())
         self._bound = None
@@ -155,6 +156,14 @@ class Solver:
     @property
     def launches(self):
         return int(self.lib.pypde_b200_launch_count(self.h))
+
+    def stiff_stats(self):
+        """k_dg_stiff's iteration counters since the solver was created (needs
+        PYPDE_B200_STIFF_STATS=1 when the solver is built): Newton iterations, evaluations
+        of the predictor's objective, inner Krylov steps, and inner steps beyond the
+        shared-memory resident basis."""
+        raw = self.read_stage('stiff_stats').view(np.uint64)
+        return dict(zip(('newton', 'obj', 'inner', 'deep'), (int(x) for x in raw)))
 
     def read_stage(self, name):
         n = c_size_t()

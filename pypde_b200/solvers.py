@@ -24,10 +24,23 @@ from pypde_b200.utils import (c_ptr, check_error, create_solver, get_cdll,
 FLUXES = {'rusanov': 0, 'roe': 1, 'osher': 2}
 
 
-def _is_second_order(F):
+def _is_second_order(F, secondOrder=None):
     """reference solvers.py:196 decides by F's arity; here the lowered function
-    carries the answer (reference style: 3 parameters; device style: 4)."""
-    return bool(getattr(F, 'second_order', False)) if F is not None else False
+    carries the answer (reference style: 3 parameters; device style: 4).  A compiled
+    image (CudaSource / DeviceFunction) shows no arity: it must say so itself
+    (`second_order=`) or the caller must (`secondOrder=`) — guessing "first order"
+    would silently zero dQ in every kernel."""
+    if F is None:
+        return False
+    if secondOrder is not None:
+        return bool(secondOrder)
+    so = getattr(F, 'second_order', None)
+    if so is None:
+        raise TypeError('pypde_b200: %s is a compiled device function, so whether F reads dQ '
+                        'cannot be seen from its arity: pass second_order=True/False to '
+                        'CudaSource / DeviceFunction, or secondOrder=True/False to the solver.'
+                        % getattr(F, 'name', 'F'))
+    return bool(so)
 
 
 def pde_solver(Q0,
@@ -43,7 +56,8 @@ def pde_solver(Q0,
                flux='rusanov',
                stiff=True,
                nThreads=-1,
-               wavespeed=None):
+               wavespeed=None,
+               secondOrder=None):
     """Solves dQ/dt + div F(Q, grad Q) + B(Q).grad Q = S(Q) with ADER-WENO on
     the GPU.  Same contract as reference pypde.pde_solver: returns an array of
     shape (ndt,) + Q0.shape; Q0 is advanced in place when it is C-contiguous.
@@ -54,6 +68,10 @@ def pde_solver(Q0,
     Jacobian + eigen-solve that the reference — and this library by default — uses
     for the CFL condition and the Rusanov dissipation, so results differ from the
     reference's at the level of its differencing noise (~1e-8 relative in dt).
+
+    `secondOrder` (not in the reference, which reads it off F's arity): needed only
+    when F is a compiled `CudaSource` / `DeviceFunction` that does not state
+    `second_order` itself; True if F reads dQ.
     """
     nX = array(Q0.shape[:-1], dtype='int32')
     ndim = len(nX)
@@ -70,7 +88,7 @@ def pde_solver(Q0,
 
     _F, _B, _S = generate_cfuncs(F, B, S, ndim, V)
 
-    secondOrder = _is_second_order(_F)
+    secondOrder = _is_second_order(_F, secondOrder)
 
     solver = create_solver()
 

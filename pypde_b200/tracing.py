@@ -15,9 +15,11 @@ Supported inside user functions: indexing / slicing / arithmetic on arrays,
 `zeros`, `ones`, `array`, `eye`, `dot`, `inner`, `outer`, `sum`, `trace`, `det`
 (up to 3 x 3), `sqrt`, `exp`, `log`, `abs`, `sin`, `cos`, `tanh`, `maximum`, `minimum`,
 `where`, `**` (small integer powers become products, as numba emits them),
-helper functions (plain or `@njit`) called with array or scalar arguments, and
-branches on the direction `d` or on constants.  A branch on a *data* value
-(`K0 if T > Ti else 0`) cannot be traced: use `where(T > Ti, K0, 0)`.  numpy
+helper functions (plain or `@njit`) called with array or scalar arguments,
+branches on the direction `d` or on constants, and branches on *data* values
+(`K0 if T > Ti else 0`, `if rho > rho0: return a` ... `return b`, if / else blocks
+of assignments, `and` / `or` / `not` of comparisons): those are rewritten on the
+source before tracing into both-arms-then-select form (see _lower_branches).  numpy
 names must be module-level imports of the function's module (imports inside the
 function body bind the real numpy and are not seen by the tracer).
 """
@@ -133,6 +135,12 @@ class Sym:
     def __ge__(self, o):
         return self._cmp('ge', o)
 
+    def __eq__(self, o):
+        return self._cmp('eq', o)
+
+    def __ne__(self, o):
+        return self._cmp('ne', o)
+
     def __bool__(self):
         raise TraceError('a branch depends on a computed value; use where(cond, a, b)')
 
@@ -150,8 +158,29 @@ class SymBool:
         self.node = node
 
     def __bool__(self):
-        raise TraceError('a branch depends on a computed value (e.g. `a if T > Ti else b`); '
-                         'write it as where(T > Ti, a, b)')
+        raise TraceError('a branch depends on a computed value in a place the tracer cannot '
+                         'lower (inside a loop, or the function\'s source is unavailable); '
+                         'write it as where(cond, a, b)')
+
+    def _logic(self, op, o):
+        if isinstance(o, SymBool):
+            return SymBool(self.node.tape.node(op, self.node, o.node))
+        if op == 'and':
+            return self if o else False
+        return True if o else self
+
+    def __and__(self, o):
+        return self._logic('and', o)
+
+    __rand__ = __and__
+
+    def __or__(self, o):
+        return self._logic('or', o)
+
+    __ror__ = __or__
+
+    def __invert__(self):
+        return SymBool(self.node.tape.node('not', self.node))
 
 
 def _map(fn, x):
@@ -363,6 +392,317 @@ _NP_IDS[id(max)] = TRACED['maximum']
 _NP_IDS[id(min)] = TRACED['minimum']
 
 
+# ---------------------------------------------------------------------------
+# Data-dependent branches.  Python's `a if c else b`, `if c:`, `and`, `or`, `not` call
+# bool(c), which a traced comparison cannot answer; the reference's own reactive Euler
+# source does exactly that (pypde/tests/reactive_euler/system.py:47 `K0 if T > Ti else 0`).
+# Before a function is traced its source is therefore rewritten (AST -> AST):
+#   a if c else b          ->  __pde_ifexp(c, lambda: a, lambda: b)
+#   x and y / x or y / not ->  __pde_and / __pde_or / __pde_not (lazy, like Python)
+#   if c: A  else: B       ->  both branches run on copies of the variables they assign,
+#                              then every such variable becomes where(c, its A value, its B value)
+#   if c: ...return r      ->  the rest of the function body is moved into both arms:
+#      rest...                 return __pde_ifexp(c, then_arm, else_arm)
+# With an ordinary bool for c (branches on `d`, on constants) the helpers do what Python
+# does, evaluating one arm only; with a traced condition both arms are evaluated and
+# merged by select — the branch-free form GPU code wants anyway.  An `if` inside a loop,
+# `with` or `try` is left alone (and reports the TraceError above if it is data dependent).
+# ---------------------------------------------------------------------------
+import ast
+import copy as _copy
+import inspect
+import textwrap
+
+
+class _Undef:
+    def __repr__(self):
+        return '<variable not assigned before a data-dependent if>'
+
+
+_UNDEF = _Undef()
+
+
+def _cp(v):
+    return v.copy() if isinstance(v, np.ndarray) else v
+
+
+def _pde_try(thunk):
+    try:
+        return _cp(thunk())
+    except NameError:
+        return _UNDEF
+
+
+def _pde_plain(c):
+    return not isinstance(c, SymBool)
+
+
+def _pde_ifexp(c, fa, fb):
+    if isinstance(c, SymBool):
+        a, b = fa(), fb()
+        if a is None or b is None:
+            raise TraceError('one arm of a data-dependent branch returns nothing')
+        return t_where(c, a, b)
+    return fa() if c else fb()
+
+
+def _pde_and(*thunks):
+    acc = True
+    for t in thunks:
+        v = t()
+        if isinstance(v, SymBool) or isinstance(acc, SymBool):
+            acc = (acc & v) if isinstance(acc, SymBool) else (v & acc)
+        else:
+            acc = v
+            if not v:
+                return v
+    return acc
+
+
+def _pde_or(*thunks):
+    acc = False
+    for t in thunks:
+        v = t()
+        if isinstance(v, SymBool) or isinstance(acc, SymBool):
+            acc = (acc | v) if isinstance(acc, SymBool) else (v | acc)
+        else:
+            acc = v
+            if v:
+                return v
+    return acc
+
+
+def _pde_not(v):
+    return ~v if isinstance(v, SymBool) else (not v)
+
+
+def _pde_restore(vals):
+    return tuple(_cp(v) for v in vals)
+
+
+def _pde_merge(c, a_vals, b_vals, names):
+    out = []
+    for a, b, n in zip(a_vals, b_vals, names):
+        if a is _UNDEF or b is _UNDEF:
+            raise TraceError('variable %r is assigned in only one arm of a data-dependent if '
+                             'and not before it' % n)
+        out.append(t_where(c, a, b))
+    return tuple(out)
+
+
+_PDE_HELPERS = {'__pde_try': _pde_try, '__pde_plain': _pde_plain, '__pde_ifexp': _pde_ifexp,
+                '__pde_and': _pde_and, '__pde_or': _pde_or, '__pde_not': _pde_not,
+                '__pde_restore': _pde_restore, '__pde_merge': _pde_merge, '__pde_cp': _cp}
+
+
+def _stored_names(stmts):
+    """Names bound or mutated (x = ..., x += ..., x[i] = ..., for x in ...) in a block, not
+    descending into nested function definitions."""
+    names = []
+
+    def target(t):
+        if isinstance(t, ast.Name):
+            if t.id not in names:
+                names.append(t.id)
+        elif isinstance(t, (ast.Tuple, ast.List)):
+            for e in t.elts:
+                target(e)
+        elif isinstance(t, (ast.Subscript, ast.Attribute, ast.Starred)):
+            target(t.value)
+
+    def visit(n):
+        if isinstance(n, (ast.FunctionDef, ast.Lambda, ast.ClassDef)):
+            return
+        if isinstance(n, ast.Assign):
+            for t in n.targets:
+                target(t)
+        elif isinstance(n, (ast.AugAssign, ast.AnnAssign, ast.For)):
+            target(n.target)
+        elif isinstance(n, ast.NamedExpr):
+            target(n.target)
+        for ch in ast.iter_child_nodes(n):
+            visit(ch)
+
+    for st in stmts:
+        visit(st)
+    return names
+
+
+def _has_return(stmts):
+    def visit(n):
+        if isinstance(n, (ast.FunctionDef, ast.Lambda, ast.ClassDef)):
+            return False
+        if isinstance(n, ast.Return):
+            return True
+        return any(visit(ch) for ch in ast.iter_child_nodes(n))
+    return any(visit(st) for st in stmts)
+
+
+def _ends_in_return(stmts):
+    if not stmts:
+        return False
+    last = stmts[-1]
+    if isinstance(last, ast.Return):
+        return True
+    if isinstance(last, ast.If):
+        return _ends_in_return(last.body) and _ends_in_return(last.orelse)
+    return False
+
+
+class _ExprRewriter(ast.NodeTransformer):
+    """IfExp / BoolOp / Not -> helper calls with lazily evaluated arms."""
+
+    @staticmethod
+    def _thunk(e):
+        return ast.Lambda(args=ast.arguments(posonlyargs=[], args=[], kwonlyargs=[],
+                                             kw_defaults=[], defaults=[]), body=e)
+
+    @staticmethod
+    def _call(name, args):
+        return ast.Call(func=ast.Name(id=name, ctx=ast.Load()), args=args, keywords=[])
+
+    def visit_IfExp(self, n):
+        self.generic_visit(n)
+        return self._call('__pde_ifexp', [n.test, self._thunk(n.body), self._thunk(n.orelse)])
+
+    def visit_BoolOp(self, n):
+        self.generic_visit(n)
+        return self._call('__pde_and' if isinstance(n.op, ast.And) else '__pde_or',
+                          [self._thunk(v) for v in n.values])
+
+    def visit_UnaryOp(self, n):
+        self.generic_visit(n)
+        if isinstance(n.op, ast.Not):
+            return self._call('__pde_not', [n.operand])
+        return n
+
+
+class _Counter:
+    def __init__(self):
+        self.n = 0
+
+    def next(self):
+        self.n += 1
+        return self.n
+
+
+def _name(id_, store=False):
+    return ast.Name(id=id_, ctx=ast.Store() if store else ast.Load())
+
+
+def _rewrite_block(stmts, bound_before, ctr):
+    """Rewrites the `if` statements of a function-body block (see the comment above).
+    bound_before: names bound earlier in the enclosing function (parameters included)."""
+    out = []
+    bound = list(bound_before)
+    for i, st in enumerate(stmts):
+        if not isinstance(st, ast.If):
+            out.append(st)
+            for nme in _stored_names([st]):
+                if nme not in bound:
+                    bound.append(nme)
+            continue
+        k = ctr.next()
+        cname = '__pde_c%d' % k
+        out.append(ast.Assign(targets=[_name(cname, True)], value=st.test))
+        rest = stmts[i + 1:]
+        if _has_return(st.body) or _has_return(st.orelse):
+            # early return: move the rest of the block into both arms
+            arms = []
+            for tag, blk in (('t', st.body), ('e', st.orelse)):
+                full = list(blk) + ([] if _ends_in_return(blk) else _copy.deepcopy(rest))
+                if not _ends_in_return(full):
+                    full = full + [ast.Return(value=ast.Constant(value=None))]
+                # variables the arm rebinds or mutates and that exist already enter as
+                # (copied) default arguments: the arm must not see the other arm's writes
+                params = [nme for nme in _stored_names(full) if nme in bound]
+                fn = ast.FunctionDef(
+                    name='__pde_%s%d' % (tag, k),
+                    args=ast.arguments(
+                        posonlyargs=[], args=[ast.arg(arg=p_) for p_ in params], kwonlyargs=[],
+                        kw_defaults=[],
+                        defaults=[_ExprRewriter._call('__pde_cp', [_name(p_)]) for p_ in params]),
+                    body=_rewrite_block(full, bound, ctr), decorator_list=[], returns=None,
+                    type_params=[])
+                out.append(fn)
+                arms.append(_name(fn.name))
+            out.append(ast.Return(value=_ExprRewriter._call('__pde_ifexp',
+                                                            [_name(cname)] + arms)))
+            return out
+        # no return inside: run both arms on copies, merge what they assign
+        names = _stored_names(st.body + st.orelse)
+        plain = ast.If(test=_name(cname), body=_rewrite_block(st.body, bound, ctr) or [ast.Pass()],
+                       orelse=_rewrite_block(st.orelse, bound, ctr))
+
+        def snap():
+            return ast.List(elts=[_ExprRewriter._call('__pde_try',
+                                                      [_ExprRewriter._thunk(_name(nme))])
+                                  for nme in names], ctx=ast.Load())
+
+        def unpack(value):
+            return ast.Assign(targets=[ast.Tuple(elts=[_name(nme, True) for nme in names],
+                                                 ctx=ast.Store())], value=value)
+
+        sname, aname = '__pde_s%d' % k, '__pde_a%d' % k
+        both = []
+        if names:
+            both.append(ast.Assign(targets=[_name(sname, True)], value=snap()))
+            both += _rewrite_block(_copy.deepcopy(st.body), bound, ctr)
+            both.append(ast.Assign(targets=[_name(aname, True)], value=snap()))
+            both.append(unpack(_ExprRewriter._call('__pde_restore', [_name(sname)])))
+            both += _rewrite_block(_copy.deepcopy(st.orelse), bound, ctr)
+            both.append(unpack(_ExprRewriter._call(
+                '__pde_merge', [_name(cname), _name(aname), snap(),
+                                ast.Tuple(elts=[ast.Constant(value=nme) for nme in names],
+                                          ctx=ast.Load())])))
+        else:
+            both.append(ast.Pass())
+        out.append(ast.If(test=_ExprRewriter._call('__pde_plain', [_name(cname)]), body=[plain],
+                          orelse=both))
+        for nme in names:
+            if nme not in bound:
+                bound.append(nme)
+    return out
+
+
+def _lower_branches(func):
+    """A copy of the Python function `func` with its data-dependent branches rewritten, or
+    None where there is nothing to rewrite (or no source to rewrite: the code object is
+    then traced as it is)."""
+    try:
+        src = textwrap.dedent(inspect.getsource(func))
+        tree = ast.parse(src)
+    except (OSError, TypeError, SyntaxError, IndentationError):
+        return None
+    fdef = next((n for n in tree.body if isinstance(n, ast.FunctionDef)), None)
+    if fdef is None or fdef.name != func.__name__:
+        return None
+    if not any(isinstance(n, (ast.If, ast.IfExp, ast.BoolOp)) or
+               (isinstance(n, ast.UnaryOp) and isinstance(n.op, ast.Not)) for n in ast.walk(fdef)):
+        return None
+    fdef.decorator_list = []
+    a = fdef.args
+    params = [x.arg for x in a.posonlyargs + a.args + a.kwonlyargs]
+    if a.vararg:
+        params.append(a.vararg.arg)
+    if a.kwarg:
+        params.append(a.kwarg.arg)
+    fdef.body = _rewrite_block(fdef.body, params, _Counter())
+    _ExprRewriter().visit(fdef)
+    # (defaults and annotations are re-attached from the original below)
+    a.defaults, a.kw_defaults = [], [None] * len(a.kwonlyargs)
+    for x in a.posonlyargs + a.args + a.kwonlyargs:
+        x.annotation = None
+    fdef.returns = None
+    mod = ast.Module(body=[fdef], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    try:
+        code = compile(mod, '<pypde_b200.tracing: %s>' % func.__name__, 'exec')
+    except (SyntaxError, ValueError, TypeError):
+        return None
+    return code, fdef.name
+
+
 def retarget(func, _seen=None):
     """A copy of `func` whose globals resolve numpy/math names to tracing versions
     and helper functions (plain or numba-jitted) to retargeted copies."""
@@ -373,10 +713,29 @@ def retarget(func, _seen=None):
     if id(func) in _seen:
         return _seen[id(func)]
     g = dict(func.__globals__)
-    new = types.FunctionType(func.__code__, g, func.__name__, func.__defaults__, func.__closure__)
+    lowered = _lower_branches(func)
+    if lowered is not None:
+        # the rewritten source is compiled against the same (retargeted) globals; closure
+        # variables of the original become globals of the copy
+        g.update(_PDE_HELPERS)
+        if func.__closure__:
+            for nme, cell in zip(func.__code__.co_freevars, func.__closure__):
+                try:
+                    g[nme] = cell.cell_contents
+                except ValueError:
+                    pass
+        ns = {}
+        exec(lowered[0], g, ns)
+        new = ns[lowered[1]]
+        new.__defaults__ = func.__defaults__
+    else:
+        new = types.FunctionType(func.__code__, g, func.__name__, func.__defaults__,
+                                 func.__closure__)
     new.__kwdefaults__ = func.__kwdefaults__
     _seen[id(func)] = new
     for name in func.__code__.co_names:
+        if name in _PDE_HELPERS:
+            continue
         if name not in func.__globals__:
             b = __builtins__ if isinstance(__builtins__, dict) else vars(__builtins__)
             if name in ('abs', 'sum', 'max', 'min') and name in b:
@@ -438,6 +797,14 @@ def emit_body(tape, outputs, out_name, indent='    '):
         elif op in _CMP:
             lines.append('%sconst bool t%d = %s %s %s;' % (indent, i, ref(args[0]), _CMP[op],
                                                            ref(args[1])))
+            continue
+        elif op in ('and', 'or'):
+            lines.append('%sconst bool t%d = %s %s %s;' % (indent, i, ref(args[0]),
+                                                           '&&' if op == 'and' else '||',
+                                                           ref(args[1])))
+            continue
+        elif op == 'not':
+            lines.append('%sconst bool t%d = !%s;' % (indent, i, ref(args[0])))
             continue
         elif op == 'select':
             expr = '%s ? %s : %s' % (ref(args[0]), ref(args[1]), ref(args[2]))

@@ -17,13 +17,19 @@ def euler_state(rho, p, vel):
     return Q
 
 
-def centres(shape):
-    return np.meshgrid(*[(np.arange(n) + 0.5) / n for n in shape], indexing='ij')
+def centres(shape, rows=None):
+    """Cell-centre coordinates in [0, 1]^ndim; rows = (r0, r1) keeps only that range of
+    axis 0 (one rank's slab of the grid `shape`)."""
+    ax = [(np.arange(n) + 0.5) / n for n in shape]
+    if rows is not None:
+        ax[0] = ax[0][rows[0]:rows[1]]
+    return np.meshgrid(*ax, indexing='ij')
 
 
-def smooth_product(shape):
-    s = np.ones(shape)
-    for x in centres(shape):
+def smooth_product(shape, rows=None):
+    xs = centres(shape, rows)
+    s = np.ones(xs[0].shape)
+    for x in xs:
         s = s * np.sin(2 * np.pi * x)
     return s
 
@@ -36,21 +42,21 @@ def sod(n=200):
     return euler_state(rho, p, [np.zeros(n)])
 
 
-def euler_smooth(shape):
+def euler_smooth(shape, rows=None):
     """The well-conditioned parity IC of SURVEY 7.3-H1."""
     nd = len(shape)
-    rho = 1 + 0.2 * smooth_product(shape)
+    rho = 1 + 0.2 * smooth_product(shape, rows)
     vel = [1.0, -0.5, 0.25][:nd]
-    return euler_state(rho, 1.0, [v * np.ones(shape) for v in vel])
+    return euler_state(rho, 1.0, [v * np.ones(rho.shape) for v in vel])
 
 
-def euler_explosion(shape):
+def euler_explosion(shape, rows=None):
     """BASELINE config 2 IC: cylindrical / spherical explosion."""
-    r2 = sum((x - 0.5)**2 for x in centres(shape))
+    r2 = sum((x - 0.5)**2 for x in centres(shape, rows))
     inside = r2 < 0.2**2
     rho = np.where(inside, 1.0, 0.125)
     p = np.where(inside, 1.0, 0.1)
-    return euler_state(rho, p, [np.zeros(shape)] * len(shape))
+    return euler_state(rho, p, [np.zeros(rho.shape)] * len(shape))
 
 
 def advect_nc_smooth(shape):
@@ -62,11 +68,12 @@ def advect_nc_smooth(shape):
     return Q
 
 
-def taylor_green(shape):
+def taylor_green(shape, rows=None):
     """BASELINE config 5 IC on [0, 2 pi]^3."""
-    x, y, z = [2 * np.pi * c for c in centres(shape)]
-    rho = np.ones(shape)
-    v = [np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z), np.zeros(shape)]
+    x, y, z = [2 * np.pi * c for c in centres(shape, rows)]
+    rho = np.ones(x.shape)
+    v = [np.sin(x) * np.cos(y) * np.cos(z), -np.cos(x) * np.sin(y) * np.cos(z),
+         np.zeros(x.shape)]
     p = 100 / G + (np.cos(2 * x) + np.cos(2 * y)) * (np.cos(2 * z) + 2) / 16
     return euler_state(rho, p, v)
 
@@ -96,16 +103,16 @@ def reactive_state(rho, p, vel, lam):
     return Q
 
 
-def reactive_disc(shape, smooth=False):
+def reactive_disc(shape, smooth=False, rows=None):
     """BASELINE config 3 IC: burnt disc (rho, p, lambda) = (2.8, 2.0, 0) in
     unburnt gas (2.0, 0.8, 1); every state has max|Q| well above 1, as the reference's
     Newton termination rule needs.  smooth=True blends the two states with a tanh."""
-    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape)))
+    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape, rows)))
     s = 0.5 * (1 - np.tanh((r - 0.25) / 0.08)) if smooth else (r < 0.25).astype(float)
     rho = 2.0 + 0.8 * s
     p = 0.8 + 1.2 * s
     lam = 1.0 - s
-    return reactive_state(rho, p, [np.zeros(shape)] * len(shape), lam)
+    return reactive_state(rho, p, [np.zeros(r.shape)] * len(shape), lam)
 
 
 def gpr_state(rho, p, vel):
@@ -122,12 +129,13 @@ def gpr_state(rho, p, vel):
     return Q
 
 
-def gpr_disc(shape, smooth=True):
+def gpr_disc(shape, smooth=True, rows=None):
     """BASELINE config 4 IC: (rho, p) = (4, 4/g) in (2, 2/g)."""
-    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape)))
+    r = np.sqrt(sum((x - 0.5)**2 for x in centres(shape, rows)))
     s = 0.5 * (1 - np.tanh((r - 0.25) / 0.1)) if smooth else (r < 0.25).astype(float)
     rho = 2.0 + 2.0 * s
-    return gpr_state(rho, rho / G, [0.1 * np.ones(shape), np.zeros(shape), np.zeros(shape)])
+    return gpr_state(rho, rho / G, [0.1 * np.ones(r.shape), np.zeros(r.shape),
+                                    np.zeros(r.shape)])
 
 
 def weno_kat_input():
@@ -220,3 +228,41 @@ def solver_cases():
                                                bts=['transitive', 'transitive'], stiff=True,
                                                flux='osher')
     return c
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs 2-5 at the parity sizes SURVEY 8d names (C2 256^2, C3 64^2, C4 32^2,
+# C5 16^3), each run for exactly K = 1, 5 and 10 steps: the final time tf[K] lies in the
+# middle of the reference's K-th step (measured with tools/golden_times.py), so both
+# sides take K steps, the last one clipped to tf (stepper.cpp:72-73).
+# ---------------------------------------------------------------------------
+def sized_bases():
+    b = {}
+    b['c2_explosion_256'] = dict(system='euler', Q0=euler_explosion((256, 256)), L=[1., 1.],
+                                 order=3, bts=['transitive', 'transitive'],
+                                 tf_guess=26 * 0.2 * 0.9 / (2 * np.sqrt(1.4) * 256),
+                                 tf={1: 0.000148563, 5: 0.00119622, 10: 0.00521785})
+    b['c3_reactive_64'] = dict(system='reactive_euler', Q0=reactive_disc((64, 64)), L=[1., 1.],
+                               order=3, bts=['transitive', 'transitive'], stiff=True,
+                               flux='osher', tf_guess=0.02,
+                               tf={1: 0.000703125, 5: 0.00615815, 10: 0.0305194})
+    b['c4_gpr_32'] = dict(system='gpr', Q0=gpr_disc((32, 32)), L=[1., 1.], order=2,
+                          bts=['transitive', 'transitive'], stiff=True, tf_guess=0.02,
+                          tf={1: 9.627e-05, 5: 0.000866593, 10: 0.00452912})
+    b['c5_taylor_green_16'] = dict(system='navier_stokes', Q0=taylor_green((16, 16, 16)),
+                                   L=[2 * np.pi] * 3, order=3, bts=['periodic'] * 3,
+                                   second_order=True, tf_guess=0.05,
+                                   tf={1: 0.00113089, 5: 0.0101782, 10: 0.0531573})
+    return b
+
+
+def sized_cases():
+    """name_K<k> -> case dict (as solver_cases) for K = 1, 5, 10."""
+    out = {}
+    for name, b in sized_bases().items():
+        for K, tf in b['tf'].items():
+            c = {k: v for k, v in b.items() if k not in ('tf', 'tf_guess')}
+            c['tf'] = tf
+            c['steps'] = K
+            out['%s_K%d' % (name, K)] = c
+    return out

@@ -58,6 +58,18 @@ def test_second_order_by_arity():
     F2, _, _ = cfuncs.generate_cfuncs(F_second, None, None, 1, 1)
     assert not _is_second_order(F1) and _is_second_order(F2)
     assert not _is_second_order(None)
+
+
+def test_compiled_flux_must_state_its_order():
+    """A compiled image shows no arity: neither CudaSource(second_order=) nor the solver's
+    secondOrder= given -> refused, never silently first order."""
+    src = 'extern "C" __device__ void user_F(double *o, const double *q, const double *dq, int d) {}'
+    with pytest.raises(TypeError):
+        _is_second_order(cfuncs.CudaSource(src))
+    assert _is_second_order(cfuncs.CudaSource(src, second_order=True))
+    assert not _is_second_order(cfuncs.CudaSource(src, second_order=False))
+    assert _is_second_order(cfuncs.CudaSource(src), secondOrder=True)
+    assert not _is_second_order(cfuncs.CudaSource(src, second_order=True), secondOrder=False)
     assert nargs(F_euler1d) == 3
 
 

@@ -9,7 +9,7 @@ Tolerances (relative L-infinity, max|a-b|/max|b|):
   * dt: 1e-7 — the reference's wave speeds are spectral radii of forward-
     difference Jacobians (h ~ 1.5e-8), which turn 1-ulp input differences into
     ~1e-8 relative differences (SURVEY 7.3-H1b);
-  * solutions after a fixed number of steps: max(1e-10, 10 x the reference's own
+  * solutions after a fixed number of steps: max(1e-10, 4 x the reference's own
     +-1 ulp self-noise on that case) — 1e-10 is the tolerance BASELINE.json states
     for non-stiff systems; the self-noise (stored with the golden fixtures) exceeds
     it on shock data and with viscous fluxes (conftest.parity_tolerance).
@@ -90,6 +90,24 @@ def test_solver_golden(golden, name):
     assert np.array_equal(Q0, out[-1])       # in-place update of Q0, as the reference
 
 
+@pytest.mark.parametrize('name', list(cases.sized_cases()))
+def test_sized_golden(golden, name):
+    """BASELINE configs 2-5 at the parity sizes of SURVEY 8d — C2 256^2 (explosion), C3 64^2
+    (stiff Newton predictor + Osher), C4 32^2 (GPR, V = 17, stiff), C5 16^3 (3-D
+    Navier-Stokes, second-order flux) — after exactly K = 1, 5 and 10 steps, against the
+    unmodified reference (tests/golden/solver_sized.npz).  At these sizes the grid-stride
+    loops, the per-warp Newton workspaces and the multi-block reductions all wrap."""
+    c = cases.sized_cases()[name]
+    out, Q0 = run_gpu(c)
+    stated = 1e-8 if c.get('stiff') else 1e-10
+    g = golden['solver_sized']
+    err, tol = rel_linf(out[0], g[name]), parity_tolerance(g, name, stated)
+    print('%s: GPU vs reference %.2e (tolerance %.2e, reference self-noise %.2e)' %
+          (name, err, tol, float(g[name + '__noise'])))
+    assert err < tol
+    assert np.array_equal(Q0, out[-1])
+
+
 @pytest.mark.parametrize('name,env', [
     ('euler2d_explosion_N3', 'PYPDE_B200_DG_NODE'), ('sod_N2', 'PYPDE_B200_DG_NODE'),
     ('euler3d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('burgers2d_N2', 'PYPDE_B200_DG_NODE'),
@@ -100,12 +118,16 @@ def test_solver_golden(golden, name):
     ('reactive1d_smooth_N3_stiff', 'PYPDE_B200_FACES_SIDE'),
     ('euler2d_explosion_N3', 'PYPDE_B200_WENO_FUSED'), ('euler2d_smooth_N2', 'PYPDE_B200_WENO_FUSED'),
     ('burgers2d_N2', 'PYPDE_B200_WENO_FUSED'), ('advect_nc_2d_N2', 'PYPDE_B200_WENO_FUSED'),
-    ('euler2d_strip_N2', 'PYPDE_B200_WENO_FUSED'), ('gpr2d_N2_stiff', 'PYPDE_B200_WENO_FUSED')])
+    ('euler2d_strip_N2', 'PYPDE_B200_WENO_FUSED'), ('gpr2d_N2_stiff', 'PYPDE_B200_WENO_FUSED'),
+    ('reactive2d_disc_N3_stiff', 'PYPDE_B200_STIFF_V1'), ('gpr2d_N2_stiff', 'PYPDE_B200_STIFF_V1'),
+    ('advect_nc_2d_N2_stiff', 'PYPDE_B200_STIFF_V1'), ('euler1d_smooth_N3_stiff', 'PYPDE_B200_STIFF_V1')])
 def test_kernel_variants_agree_bit_for_bit(name, env):
     """The node-thread predictor (k_dg_n), the fused Rusanov face kernels (k_faces_side:
     two threads per face; k_faces_fused: one) and the TMA-fed two-sweep WENO tile kernel
     (k_weno2d) run every sum in the order of the general kernels they replace (k_dg;
-    k_wavespeeds + k_faces; k_weno_sweep x 2): same bits, whole runs."""
+    k_wavespeeds + k_faces; k_weno_sweep x 2): same bits, whole runs.  So does the stiff
+    predictor with its Krylov basis in shared memory against the round-1 kernel that kept
+    it in global memory (PYPDE_B200_STIFF_V1=1)."""
     c = cases.solver_cases()[name]
     outs = []
     for val in ('1', '0'):
@@ -323,7 +345,7 @@ def test_config2_against_reference_library_128():
     err = rel_linf(out, a)
     print('config 2 at 128^2: GPU vs reference %.2e, reference self-noise %.2e' % (err, noise))
     assert np.abs(a - Q0).max() > 1e-2
-    assert err < max(1e-10, 10 * noise)
+    assert err < max(1e-10, 4 * noise)
 
 
 # ------------------------------------------------- size-independent properties

@@ -110,10 +110,85 @@ def test_traced_source_matches_python(func, kind, ndim, V, tmp_path):
             assert np.allclose(got, np.ravel(ref), rtol=1e-14, atol=1e-15)
 
 
-def test_data_dependent_branch_is_reported():
+# ---- data-dependent branches: rewritten on the source into both-arms-then-select form
+def _rate(T):                       # reference tests/reactive_euler/system.py:36-47
+    Ti = 0.25
+    K0 = 250
+    return K0 if T > Ti else 0
+
+
+def _p_ref(rho):                    # early returns, as reference tests/gpr/misc/mg.py:18-30
+    rho0 = 1.2
+    if rho > rho0:
+        return 3. * (1 / rho0 - 1 / rho) / (1 / rho0 - 0.5 * (1 / rho0 - 1 / rho))**2
+    return 3. * (rho - rho0)
+
+
+def S_branchy(Q):
+    ret = zeros(4)
+    r = Q[0]
+    T = Q[1] / r
+    ret[3] = -Q[3] * _rate(T)
+    a = 2. * r
+    if T > 0.8 and not r > 1.5:     # if / else blocks of assignments, and / not
+        a = a + Q[2]
+        ret[1] = a * T
+    else:
+        ret[1] = -a
+        ret[2] = 7.
+    if Q[2] == Q[2] or T < 0.:      # == on traced values; or
+        ret[0] = _p_ref(r)
+    if r != r:
+        ret[0] = -1.
+    return ret
+
+
+def F_branchy(Q, d):
+    ret = zeros(4)
+    v = Q[2 + d] / Q[0]             # a branch on the direction stays a Python branch
+    if d == 0:
+        ret[0] = v
+    else:
+        ret[0] = -v
+    if v > 0.:                      # early return with the rest of the body in the other arm
+        ret[1] = Q[1] * v
+        return ret
+    ret[1] = Q[3] * v
+    ret[2] = 1.
+    return ret
+
+
+@pytest.mark.parametrize('func,kind', [(S_branchy, 'S'), (F_branchy, 'F')])
+def test_data_dependent_branches_are_lowered(func, kind, tmp_path):
+    src, _ = trace_function(func, kind, 2, 4)
+    assert ' ? ' in src
+    fn = compile_host(src, kind, tmp_path, func.__name__)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        q = rng.uniform(0.2, 2.0, 4) * rng.choice([-1., 1.], 4) ** np.array([0, 0, 1, 1])
+        for d in range(2 if kind == 'F' else 1):
+            ref = func(q, d) if kind == 'F' else func(q)
+            got = call(fn, kind, q, np.zeros((2, 4)), d, 4)
+            assert np.array_equal(got, np.ravel(ref)), (q, d)
+
+
+def test_branch_assigned_in_one_arm_only_is_reported():
     def S_bad(Q):
         ret = zeros(3)
-        ret[2] = 250. if Q[1] / Q[0] > 0.25 else 0.
+        if Q[1] / Q[0] > 0.25:
+            k = 250.
+        ret[2] = k * Q[2]
+        return ret
+    with pytest.raises(TraceError, match='only one arm'):
+        trace_function(S_bad, 'S', 1, 3)
+
+
+def test_branch_inside_a_loop_is_reported():
+    def S_bad(Q):
+        ret = zeros(3)
+        for i in range(3):
+            if Q[i] > 0.25:
+                ret[i] = 1.
         return ret
     with pytest.raises(TraceError, match='where'):
         trace_function(S_bad, 'S', 1, 3)
@@ -158,7 +233,7 @@ def test_reference_example_systems_trace(tmp_path):
         from pypde.tests.euler.system import F_euler
         from pypde.tests.gpr.system import B_gpr, F_gpr, S_gpr
         from pypde.tests.navier_stokes.system import F_navier_stokes
-        from pypde.tests.reactive_euler.system import F_reactive_euler
+        from pypde.tests.reactive_euler.system import F_reactive_euler, S_reactive_euler
     finally:
         sys.path.remove(REF)
     rng = np.random.default_rng(3)
@@ -174,6 +249,8 @@ def test_reference_example_systems_trace(tmp_path):
 
     cases_ = [(F_euler, 'F', 1, 3, lambda: rng.uniform(0.5, 2., 3)),
               (F_reactive_euler, 'F', 2, 6, lambda: rng.uniform(0.5, 2., 6)),
+              # (its ignition switch `K0 if T > Ti else 0` lands on both sides over these states)
+              (S_reactive_euler, 'S', 2, 6, lambda: rng.uniform(0.5, 2., 6)),
               (F_navier_stokes, 'F', 3, 5, lambda: rng.uniform(0.5, 2., 5)),
               (F_gpr, 'F', 2, 17, gpr_state), (B_gpr, 'B', 2, 17, gpr_state),
               (S_gpr, 'S', 2, 17, gpr_state)]

@@ -1,8 +1,12 @@
 """Summarises an `ncu --set full` report: per kernel launch the duration, DRAM
 traffic, pipe utilisation, occupancy, registers and the top stall reasons; with
---json also writes {kernel: {"dram_bytes": read+write per launch (mean), ...}}.
+--into FILE --config NAME also merges, under FILE[NAME], {"source": ..., "kernels":
+{kernel: {"dram_bytes": read+write per launch (mean), "fp64_flops": 2 DFMA + DMUL + DADD
+thread instructions executed per launch, "pipe_fp64_pct": ..., "ms": ...}}} — the
+per-launch numbers bench.py's roofline object quotes for that configuration.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--json profiles/x.json] > profiles/x.txt
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--into profiles/r2_ncu_kernels.json \
+        --config c2] > profiles/x.txt
 """
 import collections
 import csv
@@ -23,6 +27,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
+        'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
+        'smsp__cycles_elapsed.max', 'lts__t_bytes.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
         'smsp__thread_inst_executed_per_inst_executed.ratio']
 stalls = [h for h in hdr if h.startswith('smsp__pcsamp_warps_issue_stalled')
@@ -41,16 +49,45 @@ for r in rows[2:]:
     print('   top stall reasons: ' + ', '.join('%s %.0f%%' % (h, 100 * v / tot) for v, h in top))
     rd = float(r[col['dram__bytes_read.sum']]) * unit_scale[units[col['dram__bytes_read.sum']]]
     wr = float(r[col['dram__bytes_write.sum']]) * unit_scale[units[col['dram__bytes_write.sum']]]
-    a = agg.setdefault(name, {'launches': 0, 'dram_bytes': 0., 'ms': 0.})
+    a = agg.setdefault(name, {'launches': 0, 'dram_bytes': 0., 'ms': 0., 'fp64_flops': 0.,
+                              'pipe_fp64_pct': 0., 'registers': 0})
     a['launches'] += 1
     a['dram_bytes'] += rd + wr
     tu = units[col['gpu__time_duration.sum']]
     a['ms'] += float(r[col['gpu__time_duration.sum']]) * {'ms': 1., 'us': 1e-3, 'ns': 1e-6,
                                                           's': 1e3}.get(tu, 1.)
+
+    def rate(op):
+        k = 'smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % op
+        return float(r[col[k]]) if k in col and r[col[k]] else 0.
+
+    if 'smsp__cycles_elapsed.max' in col:
+        cyc = float(r[col['smsp__cycles_elapsed.max']])
+        flops = (2. * rate('dfma') + rate('dmul') + rate('dadd')) * cyc
+        a['fp64_flops'] += flops
+        print('   FP64 flops executed (2 DFMA + DMUL + DADD thread inst.): %.4e  -> %.2f TFLOP/s '
+              'under ncu' % (flops, flops / (float(r[col['gpu__time_duration.sum']]) *
+                                             {'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 's': 1.}.get(tu, 1e-3))
+                             / 1e12))
+    k = 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'
+    if k in col and r[col[k]]:
+        a['pipe_fp64_pct'] += float(r[col[k]])
+    if 'launch__registers_per_thread' in col:
+        a['registers'] = int(float(r[col['launch__registers_per_thread']]))
 for a in agg.values():
-    a['dram_bytes'] /= a['launches']
-    a['ms'] /= a['launches']
-if '--json' in sys.argv:
-    with open(sys.argv[sys.argv.index('--json') + 1], 'w') as f:
-        json.dump({'source': rep, 'config': '2-D Euler 2048^2 N=3 Rusanov', 'kernels': agg}, f,
-                  indent=1)
+    for k in ('dram_bytes', 'ms', 'fp64_flops', 'pipe_fp64_pct'):
+        a[k] /= a['launches']
+if '--into' in sys.argv:
+    path = sys.argv[sys.argv.index('--into') + 1]
+    name = sys.argv[sys.argv.index('--config') + 1]
+    try:
+        with open(path) as f:
+            allc = json.load(f)
+    except (OSError, ValueError):
+        allc = {}
+    cur = allc.setdefault(name, {'source': '', 'kernels': {}})
+    cur['source'] = (cur['source'] + '; ' if cur['source'] else '') + rep + \
+        ' (ncu --set full --clock-control none)'
+    cur['kernels'].update(agg)
+    with open(path, 'w') as f:
+        json.dump(allc, f, indent=1)

@@ -415,6 +415,12 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     KernelConfig c = make_config(ndim, N, V, FLUX, STIFF, secondOrder, dF, dB, dS);
     const char *ke = getenv("PYPDE_B200_KEEP_SOLVER");
     const bool keep = !(ke && *ke == '0');
+    if (const char *pe = getenv("PYPDE_B200_PREBUILD"))
+      if (*pe == '1') { // build box: JIT into the on-disk cache before a device is asked for
+        KernelConfig cc = c;
+        choose_block_shapes(cc);
+        build_cubin(cc, dF, dB, dS);
+      }
     std::lock_guard<std::mutex> cache_lock(g_cache_mutex);
     const std::string key = solver_key(c, dF, dB, dS, _nX, _dX, CFL, _boundaryTypes);
     if (!keep || key != g_cached_key || !g_cached_solver) {

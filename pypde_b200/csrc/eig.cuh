@@ -223,6 +223,193 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 #undef A_
 }
 
+// The same iteration on the leading n x n block of a matrix with row pitch ld, n a run-time
+// value: the active block that remains after the permutation step below.
+EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int n) {
+#define A_(i, j) a[(i) * ld + (j)]
+  if (n == 1)
+    return fabs(A_(0, 0));
+  // --- Hessenberg reduction by stabilised elementary transformations
+  for (int m = 1; m < n - 1; m++) {
+    double x = 0.;
+    int i = m;
+    for (int j = m; j < n; j++)
+      if (fabs(A_(j, m - 1)) > fabs(x)) {
+        x = A_(j, m - 1);
+        i = j;
+      }
+    if (i != m) {
+      for (int j = m - 1; j < n; j++) {
+        double tmp = A_(i, j);
+        A_(i, j) = A_(m, j);
+        A_(m, j) = tmp;
+      }
+      for (int j = 0; j < n; j++) {
+        double tmp = A_(j, i);
+        A_(j, i) = A_(j, m);
+        A_(j, m) = tmp;
+      }
+    }
+    if (x != 0.) {
+      for (i = m + 1; i < n; i++) {
+        double y = A_(i, m - 1);
+        if (y != 0.) {
+          y /= x;
+          A_(i, m - 1) = y;
+          for (int j = m; j < n; j++)
+            A_(i, j) -= y * A_(m, j);
+          for (int j = 0; j < n; j++)
+            A_(j, m) += y * A_(j, i);
+        }
+      }
+    }
+  }
+  for (int i = 2; i < n; i++)
+    for (int j = 0; j < i - 1; j++)
+      A_(i, j) = 0.;
+
+  // --- QR iteration
+  double rad = 0.;
+  double anorm = 0.;
+  for (int i = 0; i < n; i++)
+    for (int j = (i > 0 ? i - 1 : 0); j < n; j++)
+      anorm += fabs(A_(i, j));
+  int nn = n - 1;
+  double t = 0.;
+  double p = 0., q = 0., r = 0., s, w, x, y, z;
+  while (nn >= 0) {
+    int its = 0;
+    int l;
+    do {
+      for (l = nn; l > 0; l--) {
+        s = fabs(A_(l - 1, l - 1)) + fabs(A_(l, l));
+        // both diagonal entries negligible against the matrix (zero, or denormal
+        // leftovers such as a fully burnt mass fraction ~1e-308): measure the
+        // subdiagonal against the norm instead — a backward error of eps ||A||
+        if (s <= DBL_EPS * anorm)
+          s = anorm;
+        if (fabs(A_(l, l - 1)) <= DBL_EPS * s) {
+          A_(l, l - 1) = 0.;
+          break;
+        }
+      }
+      x = A_(nn, nn);
+      if (l == nn) { // one real root
+        rad = fmax(rad, fabs(x + t));
+        nn--;
+      } else {
+        y = A_(nn - 1, nn - 1);
+        w = A_(nn, nn - 1) * A_(nn - 1, nn);
+        if (l == nn - 1) { // two roots
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = sqrt(fabs(q));
+          x += t;
+          if (q >= 0.) { // real pair
+            z = p + (p >= 0. ? fabs(z) : -fabs(z));
+            double r1 = x + z;
+            double r2 = r1;
+            if (z != 0.)
+              r2 = x - w / z;
+            rad = fmax(rad, fmax(fabs(r1), fabs(r2)));
+          } else { // complex pair
+            rad = fmax(rad, hypot(x + p, z));
+          }
+          nn -= 2;
+        } else { // no root yet: QR step
+          if (its >= 60) { // no convergence: fall back to a norm bound
+            return anorm;
+          }
+          if (its == 10 || its == 20) { // exceptional shift
+            t += x;
+            for (int i = 0; i <= nn; i++)
+              A_(i, i) -= x;
+            s = fabs(A_(nn, nn - 1)) + fabs(A_(nn - 1, nn - 2));
+            y = x = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          int m;
+          for (m = nn - 2; m >= l; m--) {
+            z = A_(m, m);
+            r = x - z;
+            s = y - z;
+            p = (r * s - w) / A_(m + 1, m) + A_(m, m + 1);
+            q = A_(m + 1, m + 1) - z - r - s;
+            r = A_(m + 2, m + 1);
+            s = fabs(p) + fabs(q) + fabs(r);
+            p /= s;
+            q /= s;
+            r /= s;
+            if (m == l)
+              break;
+            double uu = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
+            double vv = fabs(p) * (fabs(A_(m - 1, m - 1)) + fabs(z) +
+                                   fabs(A_(m + 1, m + 1)));
+            if (uu <= DBL_EPS * vv)
+              break;
+          }
+          for (int i = m; i < nn - 1; i++) {
+            A_(i + 2, i) = 0.;
+            if (i != m)
+              A_(i + 2, i - 1) = 0.;
+          }
+          for (int k = m; k < nn; k++) {
+            if (k != m) {
+              p = A_(k, k - 1);
+              q = A_(k + 1, k - 1);
+              r = 0.;
+              if (k + 1 != nn)
+                r = A_(k + 2, k - 1);
+              if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.) {
+                p /= x;
+                q /= x;
+                r /= x;
+              }
+            }
+            double sq = sqrt(p * p + q * q + r * r);
+            s = p >= 0. ? sq : -sq;
+            if (s != 0.) {
+              if (k == m) {
+                if (l != m)
+                  A_(k, k - 1) = -A_(k, k - 1);
+              } else
+                A_(k, k - 1) = -s * x;
+              p += s;
+              x = p / s;
+              y = q / s;
+              z = r / s;
+              q /= p;
+              r /= p;
+              for (int j = k; j <= nn; j++) {
+                p = A_(k, j) + q * A_(k + 1, j);
+                if (k + 1 != nn) {
+                  p += r * A_(k + 2, j);
+                  A_(k + 2, j) -= p * z;
+                }
+                A_(k + 1, j) -= p * y;
+                A_(k, j) -= p * x;
+              }
+              int mmin = nn < k + 3 ? nn : k + 3;
+              for (int i = l; i <= mmin; i++) {
+                p = x * A_(i, k) + y * A_(i, k + 1);
+                if (k + 1 != nn) {
+                  p += z * A_(i, k + 2);
+                  A_(i, k + 2) -= p * r;
+                }
+                A_(i, k + 1) -= p * q;
+                A_(i, k) -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l + 1 < nn);
+  }
+  return rad;
+#undef A_
+}
+
 // ---------------------------------------------------------------------------
 // D1 fast path for n <= 5 (the Euler / reactive Euler / Navier-Stokes sizes):
 // all eigenvalues from the characteristic polynomial of the trace-shifted
@@ -775,10 +962,143 @@ template <int n> EIG_FN void balance(double *a) {
   }
 }
 
+// Run-time sized balancing of the leading m x m block (row pitch ld); same steps as balance<n>.
+EIG_FN void balance_rt(double *a, const int ld, const int m) {
+  for (int sweep = 0; sweep < 6; sweep++) {
+    bool done = true;
+    for (int i = 0; i < m; i++) {
+      double c = 0., r = 0.;
+      for (int j = 0; j < m; j++)
+        if (j != i) {
+          c += fabs(a[j * ld + i]);
+          r += fabs(a[i * ld + j]);
+        }
+      if (c > 0. && r > 0. && c <= 1e300 && r <= 1e300) {
+        double g = 0.5 * r, f = 1.;
+        const double s0 = c + r;
+        int guard = 0;
+        while (c < g && guard++ < 600) {
+          f *= 2.;
+          c *= 4.;
+        }
+        g = 2. * r;
+        while (c >= g && guard++ < 1200) {
+          f *= 0.5;
+          c *= 0.25;
+        }
+        if ((c + r) / f < 0.95 * s0) {
+          done = false;
+          const double fi = 1. / f;
+          for (int j = 0; j < m; j++)
+            a[i * ld + j] *= fi;
+          for (int j = 0; j < m; j++)
+            a[j * ld + i] *= f;
+        }
+      }
+    }
+    if (done)
+      break;
+  }
+}
+
+// Larger systems (n > 5; the GPR model has n = 17): most of a conserved-variable system
+// matrix dF_d/dQ + B_d is structurally zero — the 2-D GPR matrices have 50-110 non-zeros of
+// 289 — and a third to a half of its eigenvalues sit isolated on the diagonal (the
+// distortion and thermal-impulse rows that direction d does not couple: eigenvalue v_d).
+// The permutation step of the classical balancing algorithm (Parlett & Reinsch; LAPACK
+// dgebal, job P) finds them: a row whose off-diagonal entries vanish inside the active
+// block is exchanged to its end, then a column whose off-diagonal entries vanish to its
+// front, repeatedly — an exact similarity — leaving
+//        | T1  X   Y  |
+//   P A P^T = |  0   B   Z  |     spec(A) = diag(T1) u spec(B) u diag(T2)
+//        |  0   0   T2 |
+// with T1, T2 upper triangular.  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
+// scaling, Hessenberg reduction and the QR iteration, whose cost is cubic in its size:
+// measured on B200, GPR 256^2: k_wavespeeds 11.0 -> see profiles/.  a is destroyed.
+template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
+#define A_(i, j) a[(i) * n + (j)]
+  int lo = 0, hi = n - 1;
+  double rad = 0.;
+  auto exchange = [&](int j, int m) {
+    if (j == m)
+      return;
+    for (int i = 0; i < n; i++) {
+      const double t = A_(i, j);
+      A_(i, j) = A_(i, m);
+      A_(i, m) = t;
+    }
+    for (int i = 0; i < n; i++) {
+      const double t = A_(j, i);
+      A_(j, i) = A_(m, i);
+      A_(m, i) = t;
+    }
+  };
+  // rows isolating an eigenvalue go to the end of the active block
+  for (bool found = true; found && hi >= lo;) {
+    found = false;
+    for (int j = hi; j >= lo; j--) {
+      bool zero = true;
+      for (int i = lo; i <= hi; i++)
+        if (i != j && A_(j, i) != 0.) {
+          zero = false;
+          break;
+        }
+      if (zero) {
+        exchange(j, hi);
+        rad = sel_max(rad, fabs(A_(hi, hi)));
+        hi--;
+        found = true;
+        break;
+      }
+    }
+  }
+  // columns isolating an eigenvalue go to its front
+  for (bool found = true; found && hi >= lo;) {
+    found = false;
+    for (int j = lo; j <= hi; j++) {
+      bool zero = true;
+      for (int i = lo; i <= hi; i++)
+        if (i != j && A_(i, j) != 0.) {
+          zero = false;
+          break;
+        }
+      if (zero) {
+        exchange(j, lo);
+        rad = sel_max(rad, fabs(A_(lo, lo)));
+        lo++;
+        found = true;
+        break;
+      }
+    }
+  }
+  const int m = hi - lo + 1;
+  if (m <= 0)
+    return rad;
+  if (m == 1)
+    return sel_max(rad, fabs(A_(lo, lo)));
+  // B moves to the front of the array with row pitch m (destination index <= source index,
+  // rows and columns ascending: in place), so that the iteration touches m^2 contiguous
+  // doubles of this thread's local memory instead of a window of the n^2
+  if (m < n)
+    for (int i = 0; i < m; i++)
+      for (int j = 0; j < m; j++)
+        a[i * m + j] = A_(lo + i, lo + j);
+  balance_rt(a, m, m);
+  return sel_max(rad, spectral_radius_qr_rt(a, m, m));
+#undef A_
+}
+
 // The general routine: balancing + QR iteration.  Only here does the matrix need an
 // address (the QR iteration indexes it dynamically); copying with static indices
 // keeps the caller's `a` in registers.
+#ifndef PDE_EIG_DEFLATE
+#define PDE_EIG_DEFLATE 1 // 0: n > 5 as in round 1 (scaling + QR iteration on the full matrix)
+#endif
 template <int n> EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a) {
+#if PDE_EIG_DEFLATE
+  if (n > 5)
+    return spectral_radius_deflated_qr<n>(a);
+#endif
   balance<n>(a);
   return spectral_radius_qr<n>(a);
 }

@@ -262,3 +262,83 @@ def test_abs_matrix_apply_denormal_diagonal():
     assert abs(r - 1.) < 1e-14
     r, _ = rho(M, 1)
     assert abs(r - 1.) < 1e-14
+
+
+# ---- n > 5: permutation step (isolated eigenvalues) + QR on the active block --------------
+def _fd_system_matrix(F, B, q, d, ndim):
+    """eigs/system.cpp:6-26 / NumericalDiff.h: forward-difference Jacobian + B."""
+    V = q.size
+    dq = np.zeros((ndim, V))
+    f0 = F(q, dq, d)
+    M = np.zeros((V, V))
+    for i in range(V):
+        h = 2.0**-26 * max(abs(q[i]), 1.)
+        qq = q.copy()
+        qq[i] += h
+        M[:, i] = (F(qq, dq, d) - f0) / h
+    return M + (B(q, d) if B is not None else 0.)
+
+
+@pytest.mark.parametrize('ndim', [1, 2, 3])
+def test_gpr_system_matrices(ndim):
+    """The matrices the GPR configuration (BASELINE configs[3], V = 17) actually produces:
+    at rest, in 1-D motion and in general states.  Most eigenvalues are isolated on the
+    diagonal; the deflated path must agree with LAPACK and with the full-matrix QR."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+    import cases
+    from oracle import systems as SY
+    s = SY.SYSTEMS['gpr'](ndim)
+    rng = np.random.default_rng(11 + ndim)
+    base = cases.gpr_disc((6, ) * ndim)
+    states = [base[(0, ) * ndim], base[(3, ) * ndim]]
+    for _ in range(12):
+        q = base[tuple(rng.integers(0, 6, ndim))].copy()
+        q *= 1. + 0.05 * rng.standard_normal(17)
+        q[2:5] += q[0] * 0.5 * rng.standard_normal(3)
+        q[14:17] += 0.01 * rng.standard_normal(3)
+        states.append(q)
+    active = []
+    for q in states:
+        for d in range(ndim):
+            M = _fd_system_matrix(s['F'], s['B'], q, d, ndim)
+            want = np.abs(np.linalg.eigvals(M)).max()
+            got, path = rho(M)
+            full, _ = rho(M, qr_only=1)
+            assert path == 0
+            assert abs(got - want) <= 1e-12 * want, (ndim, d, got, want)
+            assert abs(got - full) <= 1e-12 * want
+            active.append(17 - sum(1 for i in range(17)
+                                   if not np.any(np.delete(M[i], i)) or not np.any(np.delete(M[:, i], i))))
+    assert max(active) < 17          # (first sweep only: the permutation step always finds some)
+
+
+@pytest.mark.parametrize('n', [6, 9, 17])
+def test_deflation_structures(n):
+    rng = np.random.default_rng(n)
+    for trial in range(60):
+        kind = trial % 6
+        A = rng.standard_normal((n, n))
+        if kind == 0:        # upper triangular in a random symmetric permutation: all isolated
+            A = np.triu(A)
+        elif kind == 1:      # block triangular: isolated rows at the end, columns at the front
+            k1, k2 = rng.integers(1, n // 2, 2)
+            A[k1:, :k1] = 0.
+            A[:k1, :k1] = np.triu(A[:k1, :k1])
+            A[n - k2:, :n - k2] = 0.
+            A[n - k2:, n - k2:] = np.triu(A[n - k2:, n - k2:])
+        elif kind == 2:      # sparse
+            A *= rng.random((n, n)) < 0.25
+        elif kind == 3:      # zero matrix with one entry / all zeros
+            A[:] = 0.
+            if trial % 2:
+                A[rng.integers(n), rng.integers(n)] = 2.5
+        elif kind == 4:      # cyclic permutation scaled: nothing isolated, |lambda| = 3
+            A = 3. * np.roll(np.eye(n), 1, axis=1)
+        # kind 5: dense
+        p = rng.permutation(n)
+        A = A[np.ix_(p, p)]
+        want = np.abs(np.linalg.eigvals(A)).max()
+        got, _ = rho(A)
+        assert abs(got - want) <= 2e-12 * max(want, 1e-300), (n, kind, got, want)

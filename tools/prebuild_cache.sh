@@ -1,0 +1,11 @@
+#!/bin/bash
+# Build box (no GPU): JIT every kernel configuration the GPU test-suite, the benches and
+# the sweeps use into pypde_b200/build/cubin_cache (git-ignored; travels to the GPU box with
+# the gpurun snapshot), so that GPU sessions start without compiling.
+cd "$(dirname "$0")/.."
+export PYPDE_B200_CACHE=$PWD/pypde_b200/build/cubin_cache PYPDE_B200_PREBUILD=1
+rm -rf $PYPDE_B200_CACHE; mkdir -p $PYPDE_B200_CACHE; chmod 700 $PYPDE_B200_CACHE
+python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -1
+for c in c1 c2 c3 c4 c5; do python tools/prof_config.py $c 1 16 > /dev/null 2>&1; done
+for s in "$@"; do python tools/variant_sweep.py $s x 16 1 2>&1 | grep -c failed; done
+ls $PYPDE_B200_CACHE | wc -l

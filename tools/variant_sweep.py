@@ -1,0 +1,90 @@
+"""Kernel variants (selected by the library's environment switches) on one bench.py
+configuration: per-kernel ms per step, whether the result has the bits of the first
+variant, and — for the stiff set with PYPDE_B200_STIFF_STATS=1 — iteration counters per cell.
+
+    python tools/variant_sweep.py stiff  [config=c3] [size=512] [steps=4]
+    python tools/variant_sweep.py eig    [config=c4] [size=256] [steps=4]
+    python tools/variant_sweep.py faces  [config=c2] [size=2048] [steps=4]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import bench  # noqa: E402
+from pypde_b200.handle import Solver  # noqa: E402
+from pypde_b200.systems import cuda_sources  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048}[which]
+steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+cfg = bench.CONFIGS[name]
+os.environ['PYPDE_B200_QUIET'] = '1'
+F, B, S, V = cuda_sources(cfg['system'], len(cfg['shape']))
+gshape, rows, Q0, dX = bench.slab_problem(cfg, 0, 1, size)
+cells = int(np.prod(Q0.shape[:-1]))
+
+SETS = {}
+SETS['eig'] = [
+    ('round 1: QR iteration on the full matrix', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0'}),
+    ('permutation step + QR on the active block', {}),
+    ('  + ws_block 256', {'PYPDE_B200_WS_BLOCK': '256'}),
+    ('  + ws_block 128 x 2', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+    ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
+    ('  + ws_block 64 x 4', {'PYPDE_B200_WS_BLOCK': '64', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
+    ('round 1 + ws_block 128 x 2', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0',
+                                    'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+]
+SETS['faces'] = [
+    ('k_faces_side (default)', {}),
+    ('k_faces_fused', {'PYPDE_B200_FACES_SIDE': '0'}),
+]
+SETS['stiff'] = [
+    ('v1 (round 1: workspace in global memory)', {'PYPDE_B200_STIFF_V1': '1'}),
+    ('v2 default', {}),
+    ('v2 + stats', {'PYPDE_B200_STIFF_STATS': '1'}),
+    ('v2 minblocks=1 (uncapped registers)', {'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=3', {'PYPDE_B200_STIFF_KS': '3'}),
+    ('v2 KS=8', {'PYPDE_B200_STIFF_KS': '8'}),
+    ('v2 KS=8 minblocks=3', {'PYPDE_B200_STIFF_KS': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '3'}),
+    ('v2 WPB=2 minblocks=8', {'PYPDE_B200_STIFF_WPB': '2', 'PYPDE_B200_STIFF_MINBLOCKS': '8'}),
+    ('v2 WPB=8 minblocks=2', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '2'}),
+]
+ref = None
+for label, env in SETS[which]:
+    os.environ.update(env)
+    try:
+        sol = Solver(Q0.shape, None, F=F, B=B, S=S, boundaryTypes=cfg['bts'], cfl=0.9,
+                     order=cfg['order'], dX=dX, flux=cfg['flux'], stiff=cfg['stiff'])
+    except RuntimeError as ex:
+        print('%-44s failed: %s' % (label, str(ex).splitlines()[0]))
+        continue
+    finally:
+        for k in env:
+            del os.environ[k]
+    sol.set_state(Q0)
+    sol.begin(1e9)
+    for _ in range(2):
+        sol.step_async()
+    sol.sync()
+    sol.set_profiling(True)
+    for _ in range(steps):
+        sol.step_async()
+    t, dt, nan = sol.sync()
+    kt = sol.kernel_times()
+    u = sol.get_state()
+    if ref is None:
+        ref = u
+    line = '%-44s step %8.3f ms  same bits as the first: %-5s  %s' % (
+        label, sum(v[0] for v in kt.values()) / steps, np.array_equal(u, ref),
+        '  '.join('%s=%.3f' % (k.replace('k_', ''), v[0] / steps) for k, v in kt.items()
+                  if v[0] / steps > 0.02))
+    if env.get('PYPDE_B200_STIFF_STATS') == '1':
+        st = sol.stiff_stats()
+        ncw = int(np.prod([n + 2 for n in Q0.shape[:-1]])) * (steps + 2)
+        line += '  per cell: newton %.2f obj %.2f inner %.2f beyond-smem %.4f' % tuple(
+            st[k] / ncw for k in ('newton', 'obj', 'inner', 'deep'))
+    print(line, flush=True)
+    sol.close()

@@ -490,7 +490,10 @@ def main():
     # ---- device-resident arm: state lives in HBM (a torch tensor), stepped in place
     u_dev = torch.from_numpy(Q0).cuda()
     sol = Solver(Q0.shape, None, **kw)
-    stream = torch.cuda.current_stream()
+    # (a stream of its own, not the legacy default stream: small grids replay the step as a
+    #  CUDA graph, and the legacy stream cannot be captured)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sol.set_stream(stream.cuda_stream)
     sol.bind_tensor(u_dev)
     sol.begin(1e9)

@@ -248,14 +248,19 @@ void choose_block_shapes(KernelConfig &c) {
       c.stiff_stats = *e == '1';
     const long budget = 227 * 1024 / 16 / 8 - 4 * 41 - (long)(5 + c.ndim) * (long)n; // doubles
     int ks = 2;
-    while (ks < 12 && (long)(ks + 1) * (long)n + (long)(ks + 1) * (ks + 2) <= budget)
+    while (ks < 12 && (long)(ks + 1) * (long)n + (long)(ks + 1) * (ks + 4) / 2 <= budget)
       ks++;
+    // (measured on B200, C3 at 512^2: KS = 3 31.6 ms, 5 36.2, 8 36.3 per step — the inner
+    //  solves of these cells run ~26 steps deep, so a handful of resident vectors more buys
+    //  less than the L1 capacity they take from the rest of the basis)
+    if (ks > 3)
+      ks = 3;
     if (const char *e = getenv("PYPDE_B200_STIFF_KS"))
       ks = atoi(e) < 1 ? 1 : (atoi(e) > 40 ? 40 : atoi(e));
     c.stiff_ks = ks;
     auto sm_warp = [&]() {
       return c.stiff_v1 ? (size_t)(6 + c.ndim) * n * 8
-                        : ((size_t)(5 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 1) +
+                        : ((size_t)(5 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 3) / 2 +
                            4 * 41) * 8;
     };
     int wpb = 4;
@@ -272,6 +277,8 @@ void choose_block_shapes(KernelConfig &c) {
     if (const char *e = getenv("PYPDE_B200_STIFF_MINBLOCKS"))
       c.stiff_minblocks = atoi(e);
   }
+  if (const char *e = getenv("PYPDE_B200_W3_TILE"))
+    sscanf(e, "%d,%d,%d", &c.w3_ti, &c.w3_tj, &c.w3_tk);
   // tuning overrides (experiments)
   if (const char *e = getenv("PYPDE_B200_WS_BLOCK"))
     c.ws_block = atoi(e);
@@ -312,6 +319,9 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb),
           kv("PDE_STIFF_WPB", c.stiff_wpb),
+          kv("PDE_W3_TI", c.w3_ti),
+          kv("PDE_W3_TJ", c.w3_tj),
+          kv("PDE_W3_TK", c.w3_tk),
           kv("PDE_STIFF_KS", c.stiff_ks),
           kv("PDE_STIFF_MINBLOCKS", c.stiff_minblocks),
           kv("PDE_STIFF_V1", c.stiff_v1 ? 1 : 0),

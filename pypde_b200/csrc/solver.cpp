@@ -36,6 +36,64 @@ bool weno2d_tile(const KernelConfig &c, int *ti_out, int *tj_out) {
   return true;
 }
 
+// tile of k_weno3d (kernels.cuh: W3_TI, W3_TJ, W3_TK, W3_SMEM, W3_OK)
+bool weno3d_tile(const KernelConfig &c, Weno3dTile *t) {
+  if (c.ndim != 3)
+    return false;
+  const long H = 2 * (c.N - 1), N = c.N, V = c.V;
+  const long ti = c.w3_ti, tj = c.w3_tj, tk = (c.w3_tk + H) * V <= 256 ? c.w3_tk : 4;
+  const long row = (tk + H) * V;
+  const long in = (ti + H) * (tj + H) * row, a = ti * (tj + H) * (tk + H) * N * V,
+             b = ti * tj * (tk + H) * N * N * V;
+  const long smem = ((in > b ? in : b) + a) * 8 + 128;
+  if (row > 256 || smem > 200 * 1024)
+    return false;
+  if (t)
+    *t = Weno3dTile{(int)ti, (int)tj, (int)tk, (size_t)smem};
+  return true;
+}
+
+bool weno2d_map(CUtensorMap *map, CUdeviceptr ub, const long *m, const KernelConfig &c) {
+  int ti, tj;
+  const DriverApi &d = driver();
+  if (!weno2d_tile(c, &ti, &tj) || !d.TensorMapEncodeTiled)
+    return false;
+  const cuuint64_t cols = (cuuint64_t)m[1] * c.V, rows = (cuuint64_t)m[0];
+  const int H = 2 * (c.N - 1);
+  // (row pitch and base address must be multiples of 16 bytes)
+  if (cols % 2 != 0 || (ub & 15) != 0)
+    return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)((tj + H) * c.V), (cuuint32_t)(ti + H)};
+  const cuuint32_t estr[2] = {1, 1};
+  return d.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ub, dims, strides,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ub as a 3-D tensor [m0][m1][m2 V doubles]
+bool weno3d_map(CUtensorMap *map, CUdeviceptr ub, const long *m, const KernelConfig &c) {
+  Weno3dTile t;
+  const DriverApi &d = driver();
+  if (!weno3d_tile(c, &t) || !d.TensorMapEncodeTiled)
+    return false;
+  const cuuint64_t cols = (cuuint64_t)m[2] * c.V;
+  const int H = 2 * (c.N - 1);
+  if (cols % 2 != 0 || (ub & 15) != 0)
+    return false;
+  const cuuint64_t dims[3] = {cols, (cuuint64_t)m[1], (cuuint64_t)m[0]};
+  const cuuint64_t strides[2] = {cols * sizeof(double), cols * (cuuint64_t)m[1] * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)((t.tk + H) * c.V), (cuuint32_t)(t.tj + H),
+                             (cuuint32_t)(t.ti + H)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return d.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)ub, dims, strides,
+                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // kernels.cuh: DGN_OK — where k_dg_n is compiled
 bool dgn_ok(const KernelConfig &c) {
   const int Nd = ipow(c.N, c.ndim);
@@ -127,6 +185,18 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     get(k_dg_n, "k_dg_n");
   if (weno2d_tile(cfg, nullptr, nullptr))
     get(k_weno2d, "k_weno2d");
+  if (!cfg.useB && !cfg.secondOrder) // kernels.cuh: !NEED_GRAD
+    get(k_cfl_q, "k_cfl_q");
+  {
+    Weno3dTile t3;
+    if (weno3d_tile(cfg, &t3)) {
+      get(k_weno3d, "k_weno3d");
+      if (t3.smem > 48 * 1024)
+        check(d.FuncSetAttribute(k_weno3d, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                                 (int)t3.smem),
+              "cuFuncSetAttribute(k_weno3d smem)");
+    }
+  }
   if (cfg.useF && cfg.flux == 0 && !cfg.useB && !cfg.secondOrder)
     get(k_faces_side, "k_faces_side");
 }
@@ -250,23 +320,24 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     w_.alloc((size_t)ncellw_ * Nd * V * D);
   }
   traces_.alloc((size_t)ncellw_ * 2 * nd * NP * TRW * V * D);
-  // k_weno2d: TMA descriptor of ub as a 2-D tensor [nX_0+2N rows][(nX_1+2N) V doubles]
-  // (row pitch must be a multiple of 16 bytes; otherwise the two-sweep path stays)
-  if (weno2d_tile(cfg_, &weno2d_ti_, &weno2d_tj_) && mod_->k_weno2d) {
-    const char *e = getenv("PYPDE_B200_WENO_FUSED");
-    const cuuint64_t cols = (cuuint64_t)(nX[1] + 2 * N) * V, rows = (cuuint64_t)(nX[0] + 2 * N);
-    const int H = 2 * (N - 1);
-    if (!(e && *e == '0') && cols % 2 == 0 && d.TensorMapEncodeTiled) {
-      const cuuint64_t dims[2] = {cols, rows};
-      const cuuint64_t strides[1] = {cols * D};
-      const cuuint32_t box[2] = {(cuuint32_t)((weno2d_tj_ + H) * V), (cuuint32_t)(weno2d_ti_ + H)};
-      const cuuint32_t estr[2] = {1, 1};
-      CUresult r = d.TensorMapEncodeTiled(&ub_map_, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2,
-                                          (void *)ub_.p, dims, strides, box, estr,
-                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      weno2d_ = r == CUDA_SUCCESS;
+  // k_weno2d / k_weno3d: TMA descriptor of ub as a 2-D tensor [nX_0+2N rows][(nX_1+2N) V
+  // doubles] / 3-D tensor (row pitch must be a multiple of 16 bytes; otherwise the
+  // sweep-by-sweep path stays)
+  {
+    long mb[3] = {1, 1, 1};
+    for (int i = 0; i < nd; i++)
+      mb[i] = nX[i] + 2 * N;
+    if (nd == 2 && weno2d_tile(cfg_, &weno2d_ti_, &weno2d_tj_) && mod_->k_weno2d) {
+      const char *e = getenv("PYPDE_B200_WENO_FUSED");
+      weno2d_ = !(e && *e == '0') && weno2d_map(&ub_map_, ub_.p, mb, cfg_);
+      // the tile kernel also leaves the cell averages the CFL condition needs (k_cfl_q)
+      const char *q = getenv("PYPDE_B200_CFL_Q");
+      if (weno2d_ && mod_->k_cfl_q && !(q && *q == '0'))
+        qbar_.alloc((size_t)ncellw_ * V * D);
+    }
+    if (nd == 3 && mod_->k_weno3d) {
+      const char *e = getenv("PYPDE_B200_WENO3D");
+      weno3d_ = !(e && *e == '0') && weno3d_map(&ub_map_, ub_.p, mb, cfg_);
     }
   }
   if (cfg_.useF) // per trace point: lambda, [lambda_visc]
@@ -295,7 +366,7 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
     const size_t smem_warp =
         cfg_.stiff_v1 ? (6 + nd) * n * D
-                      : ((5 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 1) + 4 * 41) * D;
+                      : ((5 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 3) / 2 + 4 * 41) * D;
     if (smem_warp > 220 * 1024)
       throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
     stiff_smem_ = stiff_wpb_ * smem_warp;
@@ -400,6 +471,9 @@ void Solver::set_stream(CUstream s) {
   stream_ = s;
   own_stream_ = false;
   drop_graph();
+  // the legacy default stream cannot be captured: plain launches there
+  if (s == nullptr || s == (CUstream)0x1 /* CU_STREAM_LEGACY */)
+    graph_enabled_ = false;
 }
 
 void Solver::set_state(const double *u_host) {
@@ -477,7 +551,7 @@ unsigned Solver::grid_for(long total, unsigned block) const {
 }
 
 void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
-                    const char *name, unsigned grid_y) {
+                    const char *name, unsigned grid_y, unsigned grid_z) {
   const DriverApi &d = driver();
   Rec r{name, nullptr, nullptr};
   if (profiling_) {
@@ -485,7 +559,7 @@ void Solver::launch(CUfunction f, unsigned grid, unsigned block, size_t smem, vo
     check(d.EventCreate(&r.b, CU_EVENT_DEFAULT), "cuEventCreate");
     check(d.EventRecord(r.a, stream_), "cuEventRecord");
   }
-  check(d.LaunchKernel(f, grid, grid_y, 1, block, 1, 1, (unsigned)smem, stream_, args, nullptr),
+  check(d.LaunchKernel(f, grid, grid_y, grid_z, block, 1, 1, (unsigned)smem, stream_, args, nullptr),
         name);
   if (profiling_) {
     check(d.EventRecord(r.b, stream_), "cuEventRecord");
@@ -692,9 +766,16 @@ void Solver::step_body() {
   }
   if (weno2d_) {
     int n0 = g_.nX[0] + 2, n1 = g_.nX[1] + 2;
-    void *args[] = {&ub_map_, &w_.p, &n0, &n1};
+    void *args[] = {&ub_map_, &w_.p, &n0, &n1, &qbar_.p};
     launch(mod_->k_weno2d, (unsigned)((n0 + weno2d_ti_ - 1) / weno2d_ti_), 256, 0, args, "k_weno2d",
            (unsigned)((n1 + weno2d_tj_ - 1) / weno2d_tj_));
+  } else if (weno3d_) {
+    Weno3dTile t3;
+    weno3d_tile(cfg_, &t3);
+    int n0 = g_.nX[0] + 2, n1 = g_.nX[1] + 2, n2 = g_.nX[2] + 2;
+    void *args[] = {&ub_map_, &w_.p, &n0, &n1, &n2};
+    launch(mod_->k_weno3d, (unsigned)((n0 + t3.ti - 1) / t3.ti), 256, t3.smem, args, "k_weno3d",
+           (unsigned)((n1 + t3.tj - 1) / t3.tj), (unsigned)((n2 + t3.tk - 1) / t3.tk));
   } else {
     long shape[3];
     for (int i = 0; i < nd; i++)
@@ -712,7 +793,10 @@ void Solver::step_body() {
     }
     run_sweeps(ub_.p, shape, bufs);
   }
-  {
+  if (qbar_.p) {
+    void *args[] = {&qbar_.p, &ncellw_, &g_, &state_.p};
+    launch(mod_->k_cfl_q, grid_for(ncellw_, 128), 128, 0, args, "k_cfl_q");
+  } else {
     void *args[] = {&w_.p, &ncellw_, &g_, &state_.p};
     launch(mod_->k_cfl, grid_for(ncellw_, 128), 128, 0, args, "k_cfl");
   }
@@ -885,13 +969,57 @@ void Solver::weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim
       build_cubin(cfg, nullptr, nullptr, nullptr);
   ensure_context();
   const DriverApi &d = driver();
-  Module mod(cfg, nullptr, nullptr, nullptr);
+  // the kernel module of a (ndim, N, V) reconstruction is kept for the next call
+  static std::mutex mods_mutex;
+  static std::map<std::string, std::shared_ptr<Module>> mods;
+  std::shared_ptr<Module> modp;
+  {
+    char key[96];
+    CUcontext ctx = nullptr;
+    d.CtxGetCurrent(&ctx);
+    snprintf(key, sizeof key, "%d,%d,%d,%d,%d,%d,%p", ndim, N, V, cfg.w3_ti, cfg.w3_tj, cfg.w3_tk,
+             (void *)ctx);
+    std::lock_guard<std::mutex> lk(mods_mutex);
+    std::shared_ptr<Module> &slot = mods[key];
+    if (!slot)
+      slot = std::make_shared<Module>(cfg, nullptr, nullptr, nullptr);
+    modp = slot;
+  }
+  Module &mod = *modp;
   int sms = 148;
   long shape[3] = {1, 1, 1};
   for (int i = 0; i < ndim; i++) {
     shape[i] = nX[i];
     if (nX[i] < 2 * N - 1)
       throw std::runtime_error("pypde_b200: weno_solver needs at least 2N-1 cells per axis");
+  }
+  // the TMA-fed tile kernels (all sweeps in one pass) where they apply, as in the time step
+  CUtensorMap map;
+  const char *e2 = getenv("PYPDE_B200_WENO_FUSED"), *e3 = getenv("PYPDE_B200_WENO3D");
+  if (ndim == 2 && mod.k_weno2d && !(e2 && *e2 == '0') && weno2d_map(&map, u, shape, cfg)) {
+    int ti, tj;
+    weno2d_tile(cfg, &ti, &tj);
+    int n0 = (int)shape[0] - 2 * (N - 1), n1 = (int)shape[1] - 2 * (N - 1);
+    CUdeviceptr no_qbar = 0;
+    void *args[] = {&map, &ret, &n0, &n1, &no_qbar};
+    check(d.LaunchKernel(mod.k_weno2d, (unsigned)((n0 + ti - 1) / ti), (unsigned)((n1 + tj - 1) / tj),
+                         1, 256, 1, 1, 0, st, args, nullptr),
+          "cuLaunchKernel(k_weno2d)");
+    check(d.StreamSynchronize(st), "cuStreamSynchronize");
+    return;
+  }
+  if (ndim == 3 && mod.k_weno3d && !(e3 && *e3 == '0') && weno3d_map(&map, u, shape, cfg)) {
+    Weno3dTile t3;
+    weno3d_tile(cfg, &t3);
+    int n0 = (int)shape[0] - 2 * (N - 1), n1 = (int)shape[1] - 2 * (N - 1),
+        n2 = (int)shape[2] - 2 * (N - 1);
+    void *args[] = {&map, &ret, &n0, &n1, &n2};
+    check(d.LaunchKernel(mod.k_weno3d, (unsigned)((n0 + t3.ti - 1) / t3.ti),
+                         (unsigned)((n1 + t3.tj - 1) / t3.tj), (unsigned)((n2 + t3.tk - 1) / t3.tk),
+                         256, 1, 1, (unsigned)t3.smem, st, args, nullptr),
+          "cuLaunchKernel(k_weno3d)");
+    check(d.StreamSynchronize(st), "cuStreamSynchronize");
+    return;
   }
   DeviceBuffer buf[2];
   CUdeviceptr cur = u;
@@ -922,7 +1050,7 @@ void Solver::weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim
     cur = out;
     shape[dd] -= 2 * (N - 1);
   }
-  // (the intermediates and the module are released on return)
+  // (the intermediates are released on return)
   check(d.StreamSynchronize(st), "cuStreamSynchronize");
 }
 

@@ -30,6 +30,19 @@ struct FluxPtrs {
   CUdeviceptr f[3];
 };
 
+// Tile shapes of the TMA-fed WENO kernels (kernels.cuh: W2_* / W3_*); false where the kernel
+// is not compiled for the configuration.
+struct Weno3dTile {
+  int ti, tj, tk;
+  size_t smem;
+};
+bool weno2d_tile(const KernelConfig &c, int *ti_out, int *tj_out);
+bool weno3d_tile(const KernelConfig &c, Weno3dTile *t);
+// Tensor maps over a padded array `ub` of extents m[] (cells) x V doubles; false if TMA
+// cannot address it (odd row pitch) or the driver has no cuTensorMapEncodeTiled.
+bool weno2d_map(CUtensorMap *map, CUdeviceptr ub, const long *m, const KernelConfig &c);
+bool weno3d_map(CUtensorMap *map, CUdeviceptr ub, const long *m, const KernelConfig &c);
+
 // process-wide slab communicator (one process per GPU)
 struct Comm {
   NcclComm comm = nullptr;
@@ -61,7 +74,7 @@ public:
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
              k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr, k_dg_n = nullptr,
-             k_weno2d = nullptr, k_faces_side = nullptr;
+             k_weno2d = nullptr, k_faces_side = nullptr, k_weno3d = nullptr, k_cfl_q = nullptr;
 };
 
 class Solver {
@@ -112,7 +125,7 @@ public:
 
 private:
   void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
-              const char *name, unsigned grid_y = 1);
+              const char *name, unsigned grid_y = 1, unsigned grid_z = 1);
   bool profiling_ = false;
   struct Rec {
     const char *name;
@@ -161,11 +174,13 @@ private:
   bool weno2d_ = false;
   int weno2d_ti_ = 0, weno2d_tj_ = 0;
   CUtensorMap ub_map_;
+  // 3-D: the three sweeps in one tiled kernel fed by TMA (PYPDE_B200_WENO3D=0: three sweeps)
+  bool weno3d_ = false;
   int stiff_wpb_ = 4;
   size_t stiff_smem_ = 0; // dynamic shared memory of k_dg_stiff per block
   long stiff_blocks_ = 0;
   DeviceBuffer u_own_, uprev_, halo_lo_, halo_hi_, ub_, tmpA_, tmpB_, w_, traces_, ws_, centers_,
-      flx_[3], state_;
+      flx_[3], state_, qbar_; // qbar_: cell averages of w from k_weno2d for k_cfl_q
   CUdeviceptr u_ = 0;
   StepState *h_state_ = nullptr; // pinned
   struct SnapSlot {

@@ -78,13 +78,15 @@ def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
         assert 'Function %s:' % k in out, k
     # the specialised kernels exist exactly where the host driver looks for them
     # (solver.cpp: Module::Module): the node-thread predictor without gradient terms in the
-    # predictor, the fused Rusanov face kernel, the TMA-fed two-sweep WENO tile kernel in 2-D
+    # predictor, the fused Rusanov face kernel, the TMA-fed WENO tile kernels in 2-D and 3-D
     first_order_no_B = B is None and not getattr(F, 'second_order', False)
     assert ('Function k_dg_n:' in out) == (first_order_no_B and N >= 2 and N**ndim <= 32)
     assert 'Function k_faces_fused:' in out
     assert ('Function k_weno2d:' in out) == (ndim == 2)
-    if ndim == 2:
-        sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', 'k_weno2d', path]).decode()
+    assert ('Function k_weno3d:' in out) == (ndim == 3)
+    if ndim >= 2:
+        sass = subprocess.check_output(['cuobjdump', '-sass', '-fun', 'k_weno%dd' % ndim,
+                                        path]).decode()
         assert 'UTMALDG' in sass and 'SYNCS' in sass      # TMA bulk-tensor load + mbarrier
 
 

@@ -5,6 +5,7 @@ variant, and — for the stiff set with PYPDE_B200_STIFF_STATS=1 — iteration c
     python tools/variant_sweep.py stiff  [config=c3] [size=512] [steps=4]
     python tools/variant_sweep.py eig    [config=c4] [size=256] [steps=4]
     python tools/variant_sweep.py faces  [config=c2] [size=2048] [steps=4]
+    python tools/variant_sweep.py weno3d [config=c5] [size=128] [steps=4]   (32 x size x size)
 """
 import os
 import sys
@@ -17,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -38,19 +39,40 @@ SETS['eig'] = [
                                     'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
 ]
 SETS['faces'] = [
-    ('k_faces_side (default)', {}),
+    ('round 1 equivalents: no prefetch, k_cfl on w', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FS_PREFETCH=0',
+                                                      'PYPDE_B200_CFL_Q': '0'}),
+    ('k_faces_side prefetch + k_cfl_q (default)', {}),
+    ('  no trace prefetch', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FS_PREFETCH=0'}),
+    ('  k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),
+    ('  fs_block 128 x 4', {'PYPDE_B200_FS_BLOCK': '128', 'PYPDE_B200_FS_MINBLOCKS': '4'}),
+    ('  fs_block 512 x 1', {'PYPDE_B200_FS_BLOCK': '512', 'PYPDE_B200_FS_MINBLOCKS': '1'}),
     ('k_faces_fused', {'PYPDE_B200_FACES_SIDE': '0'}),
+]
+SETS['weno3d'] = [
+    ('three k_weno_sweep launches', {'PYPDE_B200_WENO3D': '0'}),
+    ('k_weno3d tile 4x4x8 (default)', {}),
+    ('k_weno3d tile 2x4x8', {'PYPDE_B200_W3_TILE': '2,4,8'}),
+    ('k_weno3d tile 4x4x4', {'PYPDE_B200_W3_TILE': '4,4,4'}),
+    ('k_weno3d tile 2x2x8', {'PYPDE_B200_W3_TILE': '2,2,8'}),
+    ('k_weno3d tile 8x4x8', {'PYPDE_B200_W3_TILE': '8,4,8'}),
 ]
 SETS['stiff'] = [
     ('v1 (round 1: workspace in global memory)', {'PYPDE_B200_STIFF_V1': '1'}),
-    ('v2 default', {}),
+    ('v2 default (KS=3)', {}),
     ('v2 + stats', {'PYPDE_B200_STIFF_STATS': '1'}),
-    ('v2 minblocks=1 (uncapped registers)', {'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=3', {'PYPDE_B200_STIFF_KS': '3'}),
-    ('v2 KS=8', {'PYPDE_B200_STIFF_KS': '8'}),
-    ('v2 KS=8 minblocks=3', {'PYPDE_B200_STIFF_KS': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '3'}),
-    ('v2 WPB=2 minblocks=8', {'PYPDE_B200_STIFF_WPB': '2', 'PYPDE_B200_STIFF_MINBLOCKS': '8'}),
-    ('v2 WPB=8 minblocks=2', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '2'}),
+    ('v2 KS=2', {'PYPDE_B200_STIFF_KS': '2'}),
+    ('v2 KS=1', {'PYPDE_B200_STIFF_KS': '1'}),
+    ('v2 KS=3 minblocks=1', {'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=3 WPB=8 minblocks=2', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '2'}),
+    ('v2 KS=12 (3 blocks)', {'PYPDE_B200_STIFF_KS': '12', 'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=20 WPB=2', {'PYPDE_B200_STIFF_KS': '20', 'PYPDE_B200_STIFF_WPB': '2',
+                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=31 WPB=4 (whole basis resident)', {'PYPDE_B200_STIFF_KS': '31',
+                                               'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=31 WPB=2', {'PYPDE_B200_STIFF_KS': '31', 'PYPDE_B200_STIFF_WPB': '2',
+                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=31 WPB=1', {'PYPDE_B200_STIFF_KS': '31', 'PYPDE_B200_STIFF_WPB': '1',
+                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
 ]
 ref = None
 for label, env in SETS[which]:

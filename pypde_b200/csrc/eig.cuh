@@ -1006,83 +1006,71 @@ EIG_FN void balance_rt(double *a, const int ld, const int m) {
 // 289 — and a third to a half of its eigenvalues sit isolated on the diagonal (the
 // distortion and thermal-impulse rows that direction d does not couple: eigenvalue v_d).
 // The permutation step of the classical balancing algorithm (Parlett & Reinsch; LAPACK
-// dgebal, job P) finds them: a row whose off-diagonal entries vanish inside the active
-// block is exchanged to its end, then a column whose off-diagonal entries vanish to its
-// front, repeatedly — an exact similarity — leaving
-//        | T1  X   Y  |
+// dgebal, job P) finds them: an index whose row, or whose column, vanishes off the diagonal
+// inside the active block leaves the block, repeatedly — in permuted form
+//             | T1  X   Y  |
 //   P A P^T = |  0   B   Z  |     spec(A) = diag(T1) u spec(B) u diag(T2)
-//        |  0   0   T2 |
+//             |  0   0   T2 |
 // with T1, T2 upper triangular.  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
 // scaling, Hessenberg reduction and the QR iteration, whose cost is cubic in its size:
 // measured on B200, GPR 256^2: k_wavespeeds 11.0 -> see profiles/.  a is destroyed.
 template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
 #define A_(i, j) a[(i) * n + (j)]
-  int lo = 0, hi = n - 1;
+  // Off-diagonal non-zero counts per row and per column of the active block, kept up to
+  // date as indices leave it (one pass over the matrix, then O(n) per isolated eigenvalue;
+  // no rows or columns are physically exchanged — only the spectrum is wanted, and
+  // det(B - x I) factors along a row or a column that is zero off the diagonal whichever
+  // order the indices have).
+  int nzr[n], nzc[n];
+  bool act[n];
+  for (int i = 0; i < n; i++) {
+    nzr[i] = 0;
+    nzc[i] = 0;
+    act[i] = true;
+  }
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++)
+      if (i != j && A_(i, j) != 0.) {
+        nzr[i]++;
+        nzc[j]++;
+      }
   double rad = 0.;
-  auto exchange = [&](int j, int m) {
-    if (j == m)
-      return;
-    for (int i = 0; i < n; i++) {
-      const double t = A_(i, j);
-      A_(i, j) = A_(i, m);
-      A_(i, m) = t;
-    }
-    for (int i = 0; i < n; i++) {
-      const double t = A_(j, i);
-      A_(j, i) = A_(m, i);
-      A_(m, i) = t;
-    }
-  };
-  // rows isolating an eigenvalue go to the end of the active block
-  for (bool found = true; found && hi >= lo;) {
+  int m = n;
+  for (bool found = true; found && m > 0;) {
     found = false;
-    for (int j = hi; j >= lo; j--) {
-      bool zero = true;
-      for (int i = lo; i <= hi; i++)
-        if (i != j && A_(j, i) != 0.) {
-          zero = false;
-          break;
-        }
-      if (zero) {
-        exchange(j, hi);
-        rad = sel_max(rad, fabs(A_(hi, hi)));
-        hi--;
+    for (int i = 0; i < n; i++)
+      if (act[i] && (nzr[i] == 0 || nzc[i] == 0)) {
+        rad = sel_max(rad, fabs(A_(i, i)));
+        act[i] = false;
+        m--;
+        for (int k = 0; k < n; k++)
+          if (act[k]) {
+            if (A_(k, i) != 0.)
+              nzr[k]--;
+            if (A_(i, k) != 0.)
+              nzc[k]--;
+          }
         found = true;
-        break;
       }
-    }
   }
-  // columns isolating an eigenvalue go to its front
-  for (bool found = true; found && hi >= lo;) {
-    found = false;
-    for (int j = lo; j <= hi; j++) {
-      bool zero = true;
-      for (int i = lo; i <= hi; i++)
-        if (i != j && A_(i, j) != 0.) {
-          zero = false;
-          break;
-        }
-      if (zero) {
-        exchange(j, lo);
-        rad = sel_max(rad, fabs(A_(lo, lo)));
-        lo++;
-        found = true;
-        break;
-      }
-    }
-  }
-  const int m = hi - lo + 1;
   if (m <= 0)
     return rad;
+  // the active block B, gathered to the front of the array with row pitch m (destination
+  // index <= source index with rows and columns ascending: in place), so that the iteration
+  // touches m^2 contiguous doubles of this thread's local memory
+  int idx[n];
+  {
+    int p = 0;
+    for (int i = 0; i < n; i++)
+      if (act[i])
+        idx[p++] = i;
+  }
   if (m == 1)
-    return sel_max(rad, fabs(A_(lo, lo)));
-  // B moves to the front of the array with row pitch m (destination index <= source index,
-  // rows and columns ascending: in place), so that the iteration touches m^2 contiguous
-  // doubles of this thread's local memory instead of a window of the n^2
+    return sel_max(rad, fabs(A_(idx[0], idx[0])));
   if (m < n)
     for (int i = 0; i < m; i++)
       for (int j = 0; j < m; j++)
-        a[i * m + j] = A_(lo + i, lo + j);
+        a[i * m + j] = A_(idx[i], idx[j]);
   balance_rt(a, m, m);
   return sel_max(rad, spectral_radius_qr_rt(a, m, m));
 #undef A_

@@ -235,7 +235,7 @@ void choose_block_shapes(KernelConfig &c) {
     fpb--;
   c.faces_fpb = fpb;
   // k_dg_stiff: one warp per cell.  Shared memory per warp (kernels.cuh: NK_SMEM2) =
-  // (5+ndim) n doubles of evaluation state + KS resident Krylov vectors of n doubles +
+  // (3+ndim) n doubles of evaluation state + KS resident Krylov vectors of n doubles +
   // KS Hessenberg columns + 4 x 41 doubles of Givens / least-squares data.  KS is what
   // fits with 16 warps per SM resident (the register file allows no more at 128
   // registers per thread), at least 2 and at most 12 (a Newton step of the BASELINE
@@ -246,7 +246,7 @@ void choose_block_shapes(KernelConfig &c) {
       c.stiff_v1 = *e == '1';
     if (const char *e = getenv("PYPDE_B200_STIFF_STATS"))
       c.stiff_stats = *e == '1';
-    const long budget = 227 * 1024 / 16 / 8 - 4 * 41 - (long)(5 + c.ndim) * (long)n; // doubles
+    const long budget = 227 * 1024 / 16 / 8 - 4 * 41 - (long)(3 + c.ndim) * (long)n; // doubles
     int ks = 2;
     while (ks < 12 && (long)(ks + 1) * (long)n + (long)(ks + 1) * (ks + 4) / 2 <= budget)
       ks++;
@@ -260,7 +260,7 @@ void choose_block_shapes(KernelConfig &c) {
     c.stiff_ks = ks;
     auto sm_warp = [&]() {
       return c.stiff_v1 ? (size_t)(6 + c.ndim) * n * 8
-                        : ((size_t)(5 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 3) / 2 +
+                        : ((size_t)(3 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 3) / 2 +
                            4 * 41) * 8;
     };
     int wpb = 4;

@@ -335,9 +335,16 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
       if (weno2d_ && mod_->k_cfl_q && !(q && *q == '0'))
         qbar_.alloc((size_t)ncellw_ * V * D);
     }
+    // OPT-IN (PYPDE_B200_WENO3D=1).  Measured on B200 (profiles/r2_weno3d.txt; 3-D
+    // Navier-Stokes, N = 3, 32 x 128 x 128): three k_weno_sweep launches 0.43 ms, k_weno3d
+    // 0.47-0.61 ms depending on the tile.  The reconstruction is bound by the FP64 pipe,
+    // not by HBM (63 % pipe utilisation in either form), and a tile recomputes the first two
+    // sweeps on its halo: 1.27 x the arithmetic at the 4 x 4 x 8 tile that fits shared
+    // memory, executed at the same rate.  In 2-D the halo is cheaper and the tile kernel
+    // wins (0.61 against 0.71 ms at 2048^2); in 3-D the sweeps stay the default.
     if (nd == 3 && mod_->k_weno3d) {
       const char *e = getenv("PYPDE_B200_WENO3D");
-      weno3d_ = !(e && *e == '0') && weno3d_map(&ub_map_, ub_.p, mb, cfg_);
+      weno3d_ = e && *e == '1' && weno3d_map(&ub_map_, ub_.p, mb, cfg_);
     }
   }
   if (cfg_.useF) // per trace point: lambda, [lambda_visc]
@@ -366,7 +373,7 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
     const size_t smem_warp =
         cfg_.stiff_v1 ? (6 + nd) * n * D
-                      : ((5 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 3) / 2 + 4 * 41) * D;
+                      : ((3 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 3) / 2 + 4 * 41) * D;
     if (smem_warp > 220 * 1024)
       throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
     stiff_smem_ = stiff_wpb_ * smem_warp;
@@ -1008,7 +1015,7 @@ void Solver::weno_device(CUdeviceptr u, CUdeviceptr ret, const int *nX, int ndim
     check(d.StreamSynchronize(st), "cuStreamSynchronize");
     return;
   }
-  if (ndim == 3 && mod.k_weno3d && !(e3 && *e3 == '0') && weno3d_map(&map, u, shape, cfg)) {
+  if (ndim == 3 && mod.k_weno3d && e3 && *e3 == '1' && weno3d_map(&map, u, shape, cfg)) {
     Weno3dTile t3;
     weno3d_tile(cfg, &t3);
     int n0 = (int)shape[0] - 2 * (N - 1), n1 = (int)shape[1] - 2 * (N - 1),

@@ -289,16 +289,39 @@ PDE_FN void SYS_B(double *out, const double *Q, int d) {
   double v[3];
   for (int i = 0; i < 3; i++)
     v[i] = Q[2 + i] * ir;
-  for (int i = 0; i < 17 * 17; i++)
-    out[i] = 0.;
-  for (int i = 5; i < 14; i++)
-    out[i * 17 + i] = v[d];
-  /* ret[5+d, 5+d:8+d] -= v etc., exactly as the reference example's slices */
-  for (int k = 0; k < 3; k++) {
-    out[(5 + d) * 17 + 5 + d + k] -= v[k];
-    out[(8 + d) * 17 + 8 + d + k] -= v[k];
-    out[(11 + d) * 17 + 11 + d + k] -= v[k];
+  /* straight-line zero fill: every entry that stays zero is then a compile-time constant
+     where this function is inlined, and the kernels, which skip zero entries of B, never
+     hold B as an array in local memory */
+#define GPR_Z(r)                                                                                 \
+  out[(r) * 17 + 0] = 0.; out[(r) * 17 + 1] = 0.; out[(r) * 17 + 2] = 0.; out[(r) * 17 + 3] = 0.;  \
+  out[(r) * 17 + 4] = 0.; out[(r) * 17 + 5] = 0.; out[(r) * 17 + 6] = 0.; out[(r) * 17 + 7] = 0.;  \
+  out[(r) * 17 + 8] = 0.; out[(r) * 17 + 9] = 0.; out[(r) * 17 + 10] = 0.;                        \
+  out[(r) * 17 + 11] = 0.; out[(r) * 17 + 12] = 0.; out[(r) * 17 + 13] = 0.;                      \
+  out[(r) * 17 + 14] = 0.; out[(r) * 17 + 15] = 0.; out[(r) * 17 + 16] = 0.;
+  GPR_Z(0) GPR_Z(1) GPR_Z(2) GPR_Z(3) GPR_Z(4) GPR_Z(5) GPR_Z(6) GPR_Z(7) GPR_Z(8) GPR_Z(9)
+  GPR_Z(10) GPR_Z(11) GPR_Z(12) GPR_Z(13) GPR_Z(14) GPR_Z(15) GPR_Z(16)
+#undef GPR_Z
+  const double vd = d == 0 ? v[0] : (d == 1 ? v[1] : v[2]);
+  out[5 * 17 + 5] = vd; out[6 * 17 + 6] = vd; out[7 * 17 + 7] = vd;
+  out[8 * 17 + 8] = vd; out[9 * 17 + 9] = vd; out[10 * 17 + 10] = vd;
+  out[11 * 17 + 11] = vd; out[12 * 17 + 12] = vd; out[13 * 17 + 13] = vd;
+  /* ret[5+d, 5+d:8+d] -= v etc., exactly as the reference example's slices; one
+     statically indexed block per direction */
+#define GPR_BD(D)                                                                                \
+  out[(5 + D) * 17 + 5 + D + 0] -= v[0]; out[(5 + D) * 17 + 5 + D + 1] -= v[1];                  \
+  out[(5 + D) * 17 + 5 + D + 2] -= v[2];                                                          \
+  out[(8 + D) * 17 + 8 + D + 0] -= v[0]; out[(8 + D) * 17 + 8 + D + 1] -= v[1];                  \
+  out[(8 + D) * 17 + 8 + D + 2] -= v[2];                                                          \
+  out[(11 + D) * 17 + 11 + D + 0] -= v[0]; out[(11 + D) * 17 + 11 + D + 1] -= v[1];              \
+  out[(11 + D) * 17 + 11 + D + 2] -= v[2];
+  if (d == 0) {
+    GPR_BD(0)
+  } else if (d == 1) {
+    GPR_BD(1)
+  } else {
+    GPR_BD(2)
   }
+#undef GPR_BD
 }
 PDE_FN void SYS_S(double *out, const double *Q) {
   double r = Q[0];

@@ -155,6 +155,22 @@ def test_weno_solver_on_a_cuda_tensor():
         assert np.array_equal(w_dev.cpu().numpy(), w_host)
 
 
+def test_weno3d_tile_kernel_matches_the_sweeps():
+    """k_weno3d (opt-in, PYPDE_B200_WENO3D=1: all three sweeps of a tile in one kernel, input
+    by one 3-D TMA bulk-tensor copy) gives the bits of three k_weno_sweep launches, on grids
+    that are not multiples of the tile, for the public weno_solver op."""
+    for shape, N in [((9, 10, 11, 2), 3), ((7, 6, 8, 5), 2), ((14, 9, 21, 4), 3), ((5, 5, 6, 1), 3)]:
+        u = cases.weno_random(shape, seed=sum(shape))
+        base = pypde_b200.weno_solver(u, N)
+        os.environ['PYPDE_B200_WENO3D'] = '1'
+        try:
+            tiled = pypde_b200.weno_solver(u, N)
+        finally:
+            del os.environ['PYPDE_B200_WENO3D']
+        assert np.array_equal(base, tiled), (shape, N)
+        assert rel_linf(tiled, O.weno(u, N)) < 1e-12
+
+
 def test_opt_in_analytic_wavespeed():
     """pde_solver(..., wavespeed=user_L): the analytic |v| + c replaces the finite-difference
     Jacobian eigen-solves.  Opt-in because it is NOT the reference's definition: the result

@@ -30,49 +30,39 @@ cells = int(np.prod(Q0.shape[:-1]))
 SETS = {}
 SETS['eig'] = [
     ('round 1: QR iteration on the full matrix', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0'}),
-    ('permutation step + QR on the active block', {}),
-    ('  + ws_block 256', {'PYPDE_B200_WS_BLOCK': '256'}),
-    ('  + ws_block 128 x 2', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+    ('isolated eigenvalues first, QR on the active block', {}),
     ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
-    ('  + ws_block 64 x 4', {'PYPDE_B200_WS_BLOCK': '64', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
-    ('round 1 + ws_block 128 x 2', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0',
-                                    'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+    ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
 ]
 SETS['faces'] = [
-    ('round 1 equivalents: no prefetch, k_cfl on w', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FS_PREFETCH=0',
-                                                      'PYPDE_B200_CFL_Q': '0'}),
-    ('k_faces_side prefetch + k_cfl_q (default)', {}),
-    ('  no trace prefetch', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FS_PREFETCH=0'}),
-    ('  k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),
+    ('round 1 equivalent: k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),
+    ('k_cfl_q on k_weno2d\'s cell averages (default)', {}),
     ('  fs_block 128 x 4', {'PYPDE_B200_FS_BLOCK': '128', 'PYPDE_B200_FS_MINBLOCKS': '4'}),
     ('  fs_block 512 x 1', {'PYPDE_B200_FS_BLOCK': '512', 'PYPDE_B200_FS_MINBLOCKS': '1'}),
     ('k_faces_fused', {'PYPDE_B200_FACES_SIDE': '0'}),
 ]
 SETS['weno3d'] = [
-    ('three k_weno_sweep launches', {'PYPDE_B200_WENO3D': '0'}),
-    ('k_weno3d tile 4x4x8 (default)', {}),
-    ('k_weno3d tile 2x4x8', {'PYPDE_B200_W3_TILE': '2,4,8'}),
-    ('k_weno3d tile 4x4x4', {'PYPDE_B200_W3_TILE': '4,4,4'}),
-    ('k_weno3d tile 2x2x8', {'PYPDE_B200_W3_TILE': '2,2,8'}),
-    ('k_weno3d tile 8x4x8', {'PYPDE_B200_W3_TILE': '8,4,8'}),
+    ('three k_weno_sweep launches (default)', {}),
+    ('k_weno3d tile 4x4x8', {'PYPDE_B200_WENO3D': '1'}),
+    ('k_weno3d tile 2x4x8', {'PYPDE_B200_WENO3D': '1', 'PYPDE_B200_W3_TILE': '2,4,8'}),
+    ('k_weno3d tile 4x4x4', {'PYPDE_B200_WENO3D': '1', 'PYPDE_B200_W3_TILE': '4,4,4'}),
+    ('k_weno3d tile 2x2x8', {'PYPDE_B200_WENO3D': '1', 'PYPDE_B200_W3_TILE': '2,2,8'}),
 ]
 SETS['stiff'] = [
     ('v1 (round 1: workspace in global memory)', {'PYPDE_B200_STIFF_V1': '1'}),
-    ('v2 default (KS=3)', {}),
+    ('v2 default', {}),
     ('v2 + stats', {'PYPDE_B200_STIFF_STATS': '1'}),
-    ('v2 KS=2', {'PYPDE_B200_STIFF_KS': '2'}),
     ('v2 KS=1', {'PYPDE_B200_STIFF_KS': '1'}),
-    ('v2 KS=3 minblocks=1', {'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=3 WPB=8 minblocks=2', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '2'}),
-    ('v2 KS=12 (3 blocks)', {'PYPDE_B200_STIFF_KS': '12', 'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=20 WPB=2', {'PYPDE_B200_STIFF_KS': '20', 'PYPDE_B200_STIFF_WPB': '2',
-                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=31 WPB=4 (whole basis resident)', {'PYPDE_B200_STIFF_KS': '31',
-                                               'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=31 WPB=2', {'PYPDE_B200_STIFF_KS': '31', 'PYPDE_B200_STIFF_WPB': '2',
-                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
-    ('v2 KS=31 WPB=1', {'PYPDE_B200_STIFF_KS': '31', 'PYPDE_B200_STIFF_WPB': '1',
-                        'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+    ('v2 KS=1 minblocks=5', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '5'}),
+    ('v2 KS=1 minblocks=6', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '6'}),
+    ('v2 KS=3 CGS2', {'PYPDE_B200_STIFF_KS': '3', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
+    ('v2 KS=1 CGS2', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
+    ('v2 KS=1 CGS2 minblocks=5', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '5',
+                                  'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
+    ('v2 KS=8 CGS2', {'PYPDE_B200_STIFF_KS': '8', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
+    ('v2 KS=31 CGS2 (whole basis resident)', {'PYPDE_B200_STIFF_KS': '31',
+                                              'PYPDE_B200_STIFF_MINBLOCKS': '1',
+                                              'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
 ]
 ref = None
 for label, env in SETS[which]:

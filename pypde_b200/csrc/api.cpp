@@ -61,7 +61,7 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
                         "PYPDE_B200_DG_CPB", "PYPDE_B200_FACES_FPB", "PYPDE_B200_FUSED_FACES",
                         "PYPDE_B200_FACES_SIDE", "PYPDE_B200_DG_NODE", "PYPDE_B200_WENO_FUSED",
                         "PYPDE_B200_GRAPH", "PYPDE_B200_FF_BLOCK", "PYPDE_B200_FF_MINBLOCKS",
-                        "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS", "PYPDE_B200_STIFF_V1",
+                        "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS",
                         "PYPDE_B200_STIFF_KS", "PYPDE_B200_STIFF_WPB", "PYPDE_B200_STIFF_MINBLOCKS",
                         "PYPDE_B200_STIFF_STATS", "PYPDE_B200_WENO3D", "PYPDE_B200_CFL_Q",
                         "PYPDE_B200_W3_TILE"}) {

@@ -73,6 +73,7 @@ const DriverApi &driver() {
       B(ModuleGetFunction, "cuModuleGetFunction");
       B(FuncSetAttribute, "cuFuncSetAttribute");
       B(FuncGetAttribute, "cuFuncGetAttribute");
+      B(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor");
       B(LaunchKernel, "cuLaunchKernel");
       B(GetErrorString, "cuGetErrorString");
       B(EventCreate, "cuEventCreate");

@@ -39,6 +39,7 @@ struct DriverApi {
   CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
   CUresult (*FuncGetAttribute)(int *, CUfunction_attribute, CUfunction);
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t);
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
                            unsigned, unsigned, CUstream, void **, void **);
   CUresult (*GetErrorString)(CUresult, const char **);

@@ -151,9 +151,12 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
             q = A_(m + 1, m + 1) - z - r - s;
             r = A_(m + 2, m + 1);
             s = fabs(p) + fabs(q) + fabs(r);
-            p /= s;
-            q /= s;
-            r /= s;
+            {
+              const double rs_ = 1. / s; // (one reciprocal for the three quotients: the slow
+              p *= rs_;                  //  path of div.rn.f64 — zero quotients, all over a
+              q *= rs_;                  //  sparse matrix — was 5-11 % of the QR kernels)
+              r *= rs_;
+            }
             if (m == l)
               break;
             double uu = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
@@ -175,9 +178,10 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
               if (k + 1 != nn)
                 r = A_(k + 2, k - 1);
               if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.) {
-                p /= x;
-                q /= x;
-                r /= x;
+                const double rx_ = 1. / x;
+                p *= rx_;
+                q *= rx_;
+                r *= rx_;
               }
             }
             double sq = sqrt(p * p + q * q + r * r);
@@ -189,11 +193,14 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
               } else
                 A_(k, k - 1) = -s * x;
               p += s;
-              x = p / s;
-              y = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
+              {
+                const double rs_ = 1. / s, rp_ = 1. / p;
+                x = p * rs_;
+                y = q * rs_;
+                z = r * rs_;
+                q *= rp_;
+                r *= rp_;
+              }
               for (int j = k; j <= nn; j++) {
                 p = A_(k, j) + q * A_(k + 1, j);
                 if (k + 1 != nn) {
@@ -338,9 +345,12 @@ EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int 
             q = A_(m + 1, m + 1) - z - r - s;
             r = A_(m + 2, m + 1);
             s = fabs(p) + fabs(q) + fabs(r);
-            p /= s;
-            q /= s;
-            r /= s;
+            {
+              const double rs_ = 1. / s; // (one reciprocal for the three quotients: the slow
+              p *= rs_;                  //  path of div.rn.f64 — zero quotients, all over a
+              q *= rs_;                  //  sparse matrix — was 5-11 % of the QR kernels)
+              r *= rs_;
+            }
             if (m == l)
               break;
             double uu = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
@@ -362,9 +372,10 @@ EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int 
               if (k + 1 != nn)
                 r = A_(k + 2, k - 1);
               if ((x = fabs(p) + fabs(q) + fabs(r)) != 0.) {
-                p /= x;
-                q /= x;
-                r /= x;
+                const double rx_ = 1. / x;
+                p *= rx_;
+                q *= rx_;
+                r *= rx_;
               }
             }
             double sq = sqrt(p * p + q * q + r * r);
@@ -376,11 +387,14 @@ EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int 
               } else
                 A_(k, k - 1) = -s * x;
               p += s;
-              x = p / s;
-              y = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
+              {
+                const double rs_ = 1. / s, rp_ = 1. / p;
+                x = p * rs_;
+                y = q * rs_;
+                z = r * rs_;
+                q *= rp_;
+                r *= rp_;
+              }
               for (int j = k; j <= nn; j++) {
                 p = A_(k, j) + q * A_(k + 1, j);
                 if (k + 1 != nn) {
@@ -1006,71 +1020,86 @@ EIG_FN void balance_rt(double *a, const int ld, const int m) {
 // 289 — and a third to a half of its eigenvalues sit isolated on the diagonal (the
 // distortion and thermal-impulse rows that direction d does not couple: eigenvalue v_d).
 // The permutation step of the classical balancing algorithm (Parlett & Reinsch; LAPACK
-// dgebal, job P) finds them: an index whose row, or whose column, vanishes off the diagonal
-// inside the active block leaves the block, repeatedly — in permuted form
+// dgebal, job P) finds them: a row whose off-diagonal entries vanish inside the active
+// block is exchanged to its end, then a column whose off-diagonal entries vanish to its
+// front, repeatedly — an exact similarity — leaving
 //             | T1  X   Y  |
 //   P A P^T = |  0   B   Z  |     spec(A) = diag(T1) u spec(B) u diag(T2)
 //             |  0   0   T2 |
-// with T1, T2 upper triangular.  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
+// with T1, T2 upper triangular.  (Keeping non-zero counts per row and column instead of
+// exchanging rows was measured slower on the GPU: 11.4 against 9.7 ms for the GPR wave
+// speeds at 256^2 — its gather through an index list is one more level of dynamic
+// indexing in local memory.)  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
 // scaling, Hessenberg reduction and the QR iteration, whose cost is cubic in its size:
 // measured on B200, GPR 256^2: k_wavespeeds 11.0 -> see profiles/.  a is destroyed.
 template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
 #define A_(i, j) a[(i) * n + (j)]
-  // Off-diagonal non-zero counts per row and per column of the active block, kept up to
-  // date as indices leave it (one pass over the matrix, then O(n) per isolated eigenvalue;
-  // no rows or columns are physically exchanged — only the spectrum is wanted, and
-  // det(B - x I) factors along a row or a column that is zero off the diagonal whichever
-  // order the indices have).
-  int nzr[n], nzc[n];
-  bool act[n];
-  for (int i = 0; i < n; i++) {
-    nzr[i] = 0;
-    nzc[i] = 0;
-    act[i] = true;
-  }
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < n; j++)
-      if (i != j && A_(i, j) != 0.) {
-        nzr[i]++;
-        nzc[j]++;
-      }
+  int lo = 0, hi = n - 1;
   double rad = 0.;
-  int m = n;
-  for (bool found = true; found && m > 0;) {
+  auto exchange = [&](int j, int m) {
+    if (j == m)
+      return;
+    for (int i = 0; i < n; i++) {
+      const double t = A_(i, j);
+      A_(i, j) = A_(i, m);
+      A_(i, m) = t;
+    }
+    for (int i = 0; i < n; i++) {
+      const double t = A_(j, i);
+      A_(j, i) = A_(m, i);
+      A_(m, i) = t;
+    }
+  };
+  // rows isolating an eigenvalue go to the end of the active block
+  for (bool found = true; found && hi >= lo;) {
     found = false;
-    for (int i = 0; i < n; i++)
-      if (act[i] && (nzr[i] == 0 || nzc[i] == 0)) {
-        rad = sel_max(rad, fabs(A_(i, i)));
-        act[i] = false;
-        m--;
-        for (int k = 0; k < n; k++)
-          if (act[k]) {
-            if (A_(k, i) != 0.)
-              nzr[k]--;
-            if (A_(i, k) != 0.)
-              nzc[k]--;
-          }
+    for (int j = hi; j >= lo; j--) {
+      bool zero = true;
+      for (int i = lo; i <= hi; i++)
+        if (i != j && A_(j, i) != 0.) {
+          zero = false;
+          break;
+        }
+      if (zero) {
+        exchange(j, hi);
+        rad = sel_max(rad, fabs(A_(hi, hi)));
+        hi--;
         found = true;
+        break;
       }
+    }
   }
+  // columns isolating an eigenvalue go to its front
+  for (bool found = true; found && hi >= lo;) {
+    found = false;
+    for (int j = lo; j <= hi; j++) {
+      bool zero = true;
+      for (int i = lo; i <= hi; i++)
+        if (i != j && A_(i, j) != 0.) {
+          zero = false;
+          break;
+        }
+      if (zero) {
+        exchange(j, lo);
+        rad = sel_max(rad, fabs(A_(lo, lo)));
+        lo++;
+        found = true;
+        break;
+      }
+    }
+  }
+  const int m = hi - lo + 1;
   if (m <= 0)
     return rad;
-  // the active block B, gathered to the front of the array with row pitch m (destination
-  // index <= source index with rows and columns ascending: in place), so that the iteration
-  // touches m^2 contiguous doubles of this thread's local memory
-  int idx[n];
-  {
-    int p = 0;
-    for (int i = 0; i < n; i++)
-      if (act[i])
-        idx[p++] = i;
-  }
   if (m == 1)
-    return sel_max(rad, fabs(A_(idx[0], idx[0])));
+    return sel_max(rad, fabs(A_(lo, lo)));
+  // B moves to the front of the array with row pitch m (destination index <= source index,
+  // rows and columns ascending: in place), so that the iteration touches m^2 contiguous
+  // doubles of this thread's local memory instead of a window of the n^2
   if (m < n)
     for (int i = 0; i < m; i++)
       for (int j = 0; j < m; j++)
-        a[i * m + j] = A_(idx[i], idx[j]);
+        a[i * m + j] = A_(lo + i, lo + j);
   balance_rt(a, m, m);
   return sel_max(rad, spectral_radius_qr_rt(a, m, m));
 #undef A_
@@ -1301,9 +1330,12 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
             q = A_(m + 1, m + 1) - z - r - s;
             r = A_(m + 2, m + 1);
             s = fabs(p) + fabs(q) + fabs(r);
-            p /= s;
-            q /= s;
-            r /= s;
+            {
+              const double rs_ = 1. / s; // (one reciprocal for the three quotients: the slow
+              p *= rs_;                  //  path of div.rn.f64 — zero quotients, all over a
+              q *= rs_;                  //  sparse matrix — was 5-11 % of the QR kernels)
+              r *= rs_;
+            }
             if (m == l)
               break;
             double u = fabs(A_(m, m - 1)) * (fabs(q) + fabs(r));
@@ -1324,9 +1356,10 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
               if (k + 1 != nn)
                 r = A_(k + 2, k - 1);
               if ((xx = fabs(p) + fabs(q) + fabs(r)) != 0.) {
-                p /= xx;
-                q /= xx;
-                r /= xx;
+                const double rx_ = 1. / xx;
+                p *= rx_;
+                q *= rx_;
+                r *= rx_;
               }
             }
             double sq = sqrt(p * p + q * q + r * r);
@@ -1338,11 +1371,14 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
               } else
                 A_(k, k - 1) = -s * xx;
               p += s;
-              xx = p / s;
-              yy = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
+              {
+                const double rs_ = 1. / s, rp_ = 1. / p;
+                xx = p * rs_;
+                yy = q * rs_;
+                z = r * rs_;
+                q *= rp_;
+                r *= rp_;
+              }
               for (int j = k; j < n; j++) { // row modification
                 p = A_(k, j) + q * A_(k + 1, j);
                 if (k + 1 != nn) {

@@ -235,45 +235,34 @@ void choose_block_shapes(KernelConfig &c) {
     fpb--;
   c.faces_fpb = fpb;
   // k_dg_stiff: one warp per cell.  Shared memory per warp (kernels.cuh: NK_SMEM2) =
-  // (3+ndim) n doubles of evaluation state + KS resident Krylov vectors of n doubles +
-  // KS Hessenberg columns + 4 x 41 doubles of Givens / least-squares data.  KS is what
-  // fits with 16 warps per SM resident (the register file allows no more at 128
-  // registers per thread), at least 2 and at most 12 (a Newton step of the BASELINE
-  // configurations needs 3-8 inner iterations).
+  // (3+ndim) n doubles of evaluation state + KS resident Krylov vectors of n doubles + the
+  // packed triangular factor (32 columns) + Givens / least-squares data.  KS = 1: measured
+  // on B200 (C3 at 512^2) 1 resident vector 28.4 ms per step, 2: 30.6, 3: 31.8, 8: 36.3,
+  // all 31: 61.9 — the inner solves of these cells run ~26 steps deep, the kernel lives on
+  // occupancy (16 warps per SM at 128 registers) and on L1 for the rest of the basis, and
+  // every resident vector takes from both.
   {
     const size_t n = (size_t)NT * c.V;
-    if (const char *e = getenv("PYPDE_B200_STIFF_V1"))
-      c.stiff_v1 = *e == '1';
     if (const char *e = getenv("PYPDE_B200_STIFF_STATS"))
       c.stiff_stats = *e == '1';
-    const long budget = 227 * 1024 / 16 / 8 - 4 * 41 - (long)(3 + c.ndim) * (long)n; // doubles
-    int ks = 2;
-    while (ks < 12 && (long)(ks + 1) * (long)n + (long)(ks + 1) * (ks + 4) / 2 <= budget)
-      ks++;
-    // (measured on B200, C3 at 512^2: KS = 3 31.6 ms, 5 36.2, 8 36.3 per step — the inner
-    //  solves of these cells run ~26 steps deep, so a handful of resident vectors more buys
-    //  less than the L1 capacity they take from the rest of the basis)
-    if (ks > 3)
-      ks = 3;
+    int ks = 1;
     if (const char *e = getenv("PYPDE_B200_STIFF_KS"))
       ks = atoi(e) < 1 ? 1 : (atoi(e) > 40 ? 40 : atoi(e));
     c.stiff_ks = ks;
     auto sm_warp = [&]() {
-      return c.stiff_v1 ? (size_t)(6 + c.ndim) * n * 8
-                        : ((size_t)(3 + c.ndim + c.stiff_ks) * n + (size_t)c.stiff_ks * (c.stiff_ks + 3) / 2 +
-                           4 * 41) * 8;
+      return ((size_t)(3 + c.ndim + c.stiff_ks) * n + (size_t)32 * 35 / 2 + 5 * 41 + 2) * 8;
     };
     int wpb = 4;
     if (const char *e = getenv("PYPDE_B200_STIFF_WPB"))
       wpb = atoi(e) < 1 ? 1 : atoi(e);
     while (c.stiff_ks > 1 && sm_warp() > 220 * 1024)
       c.stiff_ks--;
-    while (wpb > 1 && wpb * sm_warp() > (c.stiff_v1 ? 96 : 110) * 1024)
+    while (wpb > 1 && wpb * sm_warp() > 110 * 1024)
       wpb--;
     c.stiff_wpb = wpb;
     // 4 blocks of 4 warps per SM <-> 128 registers per thread: no spills for V <= 8 (reactive
     // Euler: 158 uncapped); larger systems (GPR, V = 17: 254 uncapped) keep the full budget
-    c.stiff_minblocks = (c.V <= 8 && wpb == 4 && !c.stiff_v1) ? 4 : 1;
+    c.stiff_minblocks = (c.V <= 8 && wpb == 4) ? 4 : 1;
     if (const char *e = getenv("PYPDE_B200_STIFF_MINBLOCKS"))
       c.stiff_minblocks = atoi(e);
   }
@@ -324,7 +313,6 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_W3_TK", c.w3_tk),
           kv("PDE_STIFF_KS", c.stiff_ks),
           kv("PDE_STIFF_MINBLOCKS", c.stiff_minblocks),
-          kv("PDE_STIFF_V1", c.stiff_v1 ? 1 : 0),
           kv("PDE_STIFF_STATS", c.stiff_stats ? 1 : 0),
           kv("PDE_WS_BLOCK", c.ws_block),
           kv("PDE_WS_MINBLOCKS", c.ws_minblocks),

@@ -21,7 +21,6 @@ struct KernelConfig {
   int stiff_ks = 6;  // Krylov vectors / Hessenberg columns k_dg_stiff keeps in shared memory
   int stiff_minblocks = 1; // its __launch_bounds__ min-blocks (register budget; set by choose_block_shapes)
   int w3_ti = 4, w3_tj = 4, w3_tk = 8; // k_weno3d tile (PYPDE_B200_W3_TILE=ti,tj,tk)
-  bool stiff_v1 = false;   // PYPDE_B200_STIFF_V1=1: the round-1 kernel (workspace in global memory)
   bool stiff_stats = false; // PYPDE_B200_STIFF_STATS=1: iteration counters (profiling)
   int ws_block = 512, ws_minblocks = 1; // k_wavespeeds launch bounds (measured best: C5 14.8 ms vs 22.1 at 256 x 2)
   int ff_block = 256, ff_minblocks = 2; // k_faces_fused launch bounds (measured best at C2)

@@ -372,23 +372,30 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     const size_t nk_work = 41 * n + 10 * n + 42 * 41 + 6 * 41;
     stiff_wpb_ = cfg_.stiff_wpb; // = PDE_STIFF_WPB of the compiled kernel
     const size_t smem_warp =
-        cfg_.stiff_v1 ? (6 + nd) * n * D
-                      : ((3 + nd + cfg_.stiff_ks) * n + (size_t)cfg_.stiff_ks * (cfg_.stiff_ks + 3) / 2 + 4 * 41) * D;
+        ((3 + nd + cfg_.stiff_ks) * n + (size_t)32 * 35 / 2 + 5 * 41 + 2) * D;
     if (smem_warp > 220 * 1024)
       throw std::runtime_error("pypde_b200: stiff predictor working set exceeds shared memory");
     stiff_smem_ = stiff_wpb_ * smem_warp;
+    if (stiff_smem_ > 48 * 1024)
+      check(d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
+                               (int)stiff_smem_),
+            "cuFuncSetAttribute(k_dg_stiff smem)");
+    // As many blocks as are resident at once, no more: the cells come from a queue, and the
+    // global workspace (one slice per warp of the grid) then stays within L2 — ncu on a
+    // grid of twice that size: 22 GB of workspace written through to DRAM per launch.
     long blocks = (ncellw_ + stiff_wpb_ - 1) / stiff_wpb_;
-    long cap = (long)sms_ * 8;
+    int per_sm = 0;
+    if (d.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mod_->k_dg_stiff, 32 * stiff_wpb_,
+                                                    stiff_smem_) != CUDA_SUCCESS ||
+        per_sm < 1)
+      per_sm = 4;
+    long cap = (long)sms_ * per_sm;
     stiff_blocks_ = blocks < cap ? blocks : cap;
     // (+ 64 bytes: the iteration counters of PDE_STIFF_STATS)
     stiff_work_.alloc((size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D + 64);
     check(d.MemsetD8Async(stiff_work_.p + (size_t)stiff_blocks_ * stiff_wpb_ * nk_work * D, 0, 64,
                           stream_),
           "cuMemsetD8Async(stiff stats)");
-    if (stiff_smem_ > 48 * 1024)
-      check(d.FuncSetAttribute(mod_->k_dg_stiff, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                               (int)stiff_smem_),
-            "cuFuncSetAttribute(k_dg_stiff smem)");
   }
   // dynamic shared memory opt-in
   const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;

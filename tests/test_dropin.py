@@ -1,6 +1,6 @@
 """The literal drop-in claim of INTEGRATION.md §1: the reference's OWN Python front end —
 pypde/__init__.py, solvers.py, utils.py, byte-compiled unmodified by `make -C oracle
-frontend` into oracle/_ref/pypde/ — runs over this repository's library when
+frontend` into oracle/_ref/pypde/*.pyc.bin — runs over this repository's library when
 
   * pypde_b200/build/libpypde.so is placed where reference utils.py:69-80 looks for it
     (<pypde package>/build/libpypde.so), and
@@ -24,7 +24,7 @@ from conftest import parity_tolerance, rel_linf
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FRONT = os.path.join(ROOT, 'oracle', '_ref', 'pypde')
 
-needs_frontend = pytest.mark.skipif(not os.path.exists(os.path.join(FRONT, 'solvers.pyc')),
+needs_frontend = pytest.mark.skipif(not os.path.exists(os.path.join(FRONT, 'solvers.pyc.bin')),
                                     reason='oracle/_ref/pypde not built (make -C oracle frontend)')
 
 
@@ -45,8 +45,9 @@ def reference_front_end(tmp_path):
     from pypde_b200 import cfuncs
     from pypde_b200.utils import lib_path
     pkg = tmp_path / 'pypde'
-    shutil.copytree(FRONT, pkg)
     os.makedirs(pkg / 'build')
+    for m in ('__init__', 'solvers', 'utils'):       # (*.pyc.bin: see oracle/Makefile)
+        shutil.copy(os.path.join(FRONT, m + '.pyc.bin'), pkg / (m + '.pyc'))
     os.symlink(lib_path(), pkg / 'build' / 'libpypde.so')
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'pypde' or
              k.startswith('pypde.')}

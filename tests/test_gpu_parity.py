@@ -121,17 +121,13 @@ def test_sized_golden(golden, name):
     ('euler2d_strip_N2', 'PYPDE_B200_WENO_FUSED'), ('gpr2d_N2_stiff', 'PYPDE_B200_WENO_FUSED'),
     ('euler3d_smooth_N2', 'PYPDE_B200_WENO3D'), ('ns3d_taylor_green_N3', 'PYPDE_B200_WENO3D'),
     ('euler2d_explosion_N3', 'PYPDE_B200_CFL_Q'), ('burgers2d_N2', 'PYPDE_B200_CFL_Q'),
-    ('euler2d_strip_N2', 'PYPDE_B200_CFL_Q'),
-    ('reactive2d_disc_N3_stiff', 'PYPDE_B200_STIFF_V1'), ('gpr2d_N2_stiff', 'PYPDE_B200_STIFF_V1'),
-    ('advect_nc_2d_N2_stiff', 'PYPDE_B200_STIFF_V1'), ('euler1d_smooth_N3_stiff', 'PYPDE_B200_STIFF_V1')])
+    ('euler2d_strip_N2', 'PYPDE_B200_CFL_Q')])
 def test_kernel_variants_agree_bit_for_bit(name, env):
     """The node-thread predictor (k_dg_n), the fused Rusanov face kernels (k_faces_side:
     two threads per face; k_faces_fused: one), the TMA-fed WENO tile kernels (k_weno2d,
     k_weno3d) and the CFL kernel that reads k_weno2d's cell averages (k_cfl_q) run every
     sum in the order of the general kernels they replace (k_dg; k_wavespeeds + k_faces;
-    k_weno_sweep x ndim; k_cfl): same bits, whole runs.  So does the stiff
-    predictor with its Krylov basis in shared memory against the round-1 kernel that kept
-    it in global memory (PYPDE_B200_STIFF_V1=1)."""
+    k_weno_sweep x ndim; k_cfl): same bits, whole runs."""
     c = cases.solver_cases()[name]
     outs = []
     for val in ('1', '0'):

@@ -49,20 +49,12 @@ SETS['weno3d'] = [
     ('k_weno3d tile 2x2x8', {'PYPDE_B200_WENO3D': '1', 'PYPDE_B200_W3_TILE': '2,2,8'}),
 ]
 SETS['stiff'] = [
-    ('v1 (round 1: workspace in global memory)', {'PYPDE_B200_STIFF_V1': '1'}),
-    ('v2 default', {}),
-    ('v2 + stats', {'PYPDE_B200_STIFF_STATS': '1'}),
-    ('v2 KS=1', {'PYPDE_B200_STIFF_KS': '1'}),
-    ('v2 KS=1 minblocks=5', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '5'}),
-    ('v2 KS=1 minblocks=6', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '6'}),
-    ('v2 KS=3 CGS2', {'PYPDE_B200_STIFF_KS': '3', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
-    ('v2 KS=1 CGS2', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
-    ('v2 KS=1 CGS2 minblocks=5', {'PYPDE_B200_STIFF_KS': '1', 'PYPDE_B200_STIFF_MINBLOCKS': '5',
-                                  'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
-    ('v2 KS=8 CGS2', {'PYPDE_B200_STIFF_KS': '8', 'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
-    ('v2 KS=31 CGS2 (whole basis resident)', {'PYPDE_B200_STIFF_KS': '31',
-                                              'PYPDE_B200_STIFF_MINBLOCKS': '1',
-                                              'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_CGS2=1'}),
+    ('default (1 resident Krylov vector, 4 x 4 warps, 128 registers)', {}),
+    ('+ stats', {'PYPDE_B200_STIFF_STATS': '1'}),
+    ('KS=2', {'PYPDE_B200_STIFF_KS': '2'}),
+    ('KS=3', {'PYPDE_B200_STIFF_KS': '3'}),
+    ('WPB=8 minblocks=2', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '2'}),
+    ('WPB=2 minblocks=8', {'PYPDE_B200_STIFF_WPB': '2', 'PYPDE_B200_STIFF_MINBLOCKS': '8'}),
 ]
 ref = None
 for label, env in SETS[which]:

@@ -451,12 +451,15 @@ def main():
         names = ([] if args.slab_checks == 'none' else
                  list(SLAB_CHECKS) if args.slab_checks == 'all' else args.slab_checks.split(','))
         names = [n for n in names if SLAB_CHECKS[n][1][0] >= world * SLAB_CHECKS[n][2]]
-        undivided = slab_checks_undivided(names) if rank == 0 else None
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):   # (pde_solver prints like the reference)
+            undivided = slab_checks_undivided(names) if rank == 0 else None
         dist.barrier()
         if not replica or names:
             comm_init_from_torch()
         if names:
-            slab_res = slab_checks_divided(names, undivided, rank, world, dist)
+            with contextlib.redirect_stdout(sys.stderr):
+                slab_res = slab_checks_divided(names, undivided, rank, world, dist)
         if replica:
             from pypde_b200.handle import _lib
             _lib().pypde_b200_comm_finalize()

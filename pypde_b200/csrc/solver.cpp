@@ -197,7 +197,7 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
               "cuFuncSetAttribute(k_weno3d smem)");
     }
   }
-  if (cfg.useF && cfg.flux == 0 && !cfg.useB && !cfg.secondOrder)
+  if (cfg.useF && cfg.flux == 0 && !cfg.useB)
     get(k_faces_side, "k_faces_side");
 }
 

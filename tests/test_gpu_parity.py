@@ -112,7 +112,8 @@ def test_sized_golden(golden, name):
     ('euler2d_explosion_N3', 'PYPDE_B200_DG_NODE'), ('sod_N2', 'PYPDE_B200_DG_NODE'),
     ('euler3d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('burgers2d_N2', 'PYPDE_B200_DG_NODE'),
     ('euler2d_explosion_N3', 'PYPDE_B200_FUSED_FACES'), ('sod_N2', 'PYPDE_B200_FUSED_FACES'),
-    ('euler3d_smooth_N2', 'PYPDE_B200_FUSED_FACES'),
+    ('euler3d_smooth_N2', 'PYPDE_B200_FUSED_FACES'), ('ns2d_smooth_N2', 'PYPDE_B200_FUSED_FACES'),
+    ('ns3d_taylor_green_N3', 'PYPDE_B200_FUSED_FACES'),
     ('euler2d_explosion_N3', 'PYPDE_B200_FACES_SIDE'), ('sod_N2', 'PYPDE_B200_FACES_SIDE'),
     ('euler3d_smooth_N2', 'PYPDE_B200_FACES_SIDE'), ('burgers2d_N2', 'PYPDE_B200_FACES_SIDE'),
     ('reactive1d_smooth_N3_stiff', 'PYPDE_B200_FACES_SIDE'),

@@ -1,19 +1,19 @@
 #!/bin/bash
-# round 2, GPU session C (8 GPUs of one box): C4 strong scaling, C5 at 256^3 on 8 GPUs,
+# round 2, GPU session D2 (8 GPUs of one box): C4 strong scaling, C5 at 256^3 on 8 GPUs,
 # C2 weak scaling with the slab bit-identity checks, all through bench.py under torchrun
 export PYPDE_B200_CACHE=$PWD/pypde_b200/build/cubin_cache
 chmod 700 $PYPDE_B200_CACHE 2>/dev/null
 O=gpurun_out
 mkdir -p $O
-nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8 > $O/r2c_gpus.txt
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8 > $O/r2m_gpus.txt
 run() { # run N port config [extra args...]
   local n=$1 port=$2 cfg=$3; shift 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
     --master-port $port bench.py --gpus $n --config $cfg --no-cpu-baseline "$@" \
-    > $O/r2c_${cfg}_${n}gpu.json 2> $O/r2c_${cfg}_${n}gpu.err
-  python - <<PY || tail -5 $O/r2c_${cfg}_${n}gpu.err
+    > $O/r2m_${cfg}_${n}gpu.json 2> $O/r2m_${cfg}_${n}gpu.err
+  python - <<PY || tail -5 $O/r2m_${cfg}_${n}gpu.err
 import json
-d = json.load(open('$O/r2c_${cfg}_${n}gpu.json'))
+d = json.load(open('$O/r2m_${cfg}_${n}gpu.json'))
 print('$cfg x$n', '%.3e' % d['value'], 'ms/step %.3f' % d['ms_per_step'], 'e2e %.3e' % d['e2e']['value'],
       'slab_bit_identical', d.get('slab_bit_identical'),
       {k: v['bit_identical'] for k, v in (d.get('slab_checks') or {}).items()})

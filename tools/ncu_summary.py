@@ -49,6 +49,10 @@ for r in rows[2:]:
     print('   top stall reasons: ' + ', '.join('%s %.0f%%' % (h, 100 * v / tot) for v, h in top))
     rd = float(r[col['dram__bytes_read.sum']]) * unit_scale[units[col['dram__bytes_read.sum']]]
     wr = float(r[col['dram__bytes_write.sum']]) * unit_scale[units[col['dram__bytes_write.sum']]]
+    if rd != rd or wr != wr:
+        # (ncu occasionally loses a multi-pass launch: all of its counters read nan)
+        print('   (incomplete capture: not averaged)')
+        continue
     a = agg.setdefault(name, {'launches': 0, 'dram_bytes': 0., 'ms': 0., 'fp64_flops': 0.,
                               'pipe_fp64_pct': 0., 'registers': 0})
     a['launches'] += 1

@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -33,6 +33,16 @@ SETS['eig'] = [
     ('isolated eigenvalues first, QR on the active block', {}),
     ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
     ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+]
+SETS['c5'] = [
+    ('k_wavespeeds + k_faces, k_dg 1 cell per block (default)', {}),
+    ('k_faces_side for the second-order flux', {'PYPDE_B200_FUSED_FACES': '1'}),
+    ('  fs_block 128 x 4', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '128',
+                            'PYPDE_B200_FS_MINBLOCKS': '4'}),
+    ('  fs_block 512 x 1', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '512',
+                            'PYPDE_B200_FS_MINBLOCKS': '1'}),
+    ('k_dg 2 cells per block', {'PYPDE_B200_DG_CPB': '2'}),
+    ('k_dg 3 cells per block', {'PYPDE_B200_DG_CPB': '3'}),
 ]
 SETS['faces'] = [
     ('round 1 equivalent: k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),

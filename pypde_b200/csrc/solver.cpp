@@ -104,6 +104,16 @@ bool dgn_ok(const KernelConfig &c) {
   return (long)cpw * sm_cell * 8 <= 48 * 1024;
 }
 
+// kernels.cuh: DGG_OK — where k_dg_g is compiled
+bool dgg_ok(const KernelConfig &c) {
+  const int Nd = ipow(c.N, c.ndim);
+  if (!(c.useB || c.secondOrder) || c.N < 2 || Nd > 32)
+    return false;
+  const int cpw = 32 / Nd, qs = c.N * c.V * Nd, raw = 2 * qs + c.ndim * qs;
+  const int sm_cell = raw + ((Nd % 16) + 16 - (raw % 16)) % 16;
+  return (long)cpw * sm_cell * 8 <= 48 * 1024;
+}
+
 void check(CUresult r, const char *what) {
   if (r == CUDA_SUCCESS)
     return;
@@ -183,6 +193,8 @@ Module::Module(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
     get(k_faces_fused, "k_faces_fused");
   if (dgn_ok(cfg))
     get(k_dg_n, "k_dg_n");
+  if (dgg_ok(cfg))
+    get(k_dg_g, "k_dg_g");
   if (weno2d_tile(cfg, nullptr, nullptr))
     get(k_weno2d, "k_weno2d");
   if (!cfg.useB && !cfg.secondOrder) // kernels.cuh: !NEED_GRAD
@@ -838,6 +850,15 @@ void Solver::step_body() {
       nblocks = cap;
     void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
     launch(mod_->k_dg_n, (unsigned)nblocks, (unsigned)(cpw * Nd), 0, args, "k_dg_n");
+  } else if (node_dg_ && mod_->k_dg_g) {
+    // the same with gradient terms (B, second-order flux)
+    const int cpw = 32 / Nd;
+    long nblocks = (ncellw_ + cpw - 1) / cpw;
+    long cap = (long)sms_ * 32;
+    if (nblocks > cap)
+      nblocks = cap;
+    void *args[] = {&w_.p, &traces_.p, &centers_.p, &ncellw_, &g_, &state_.p};
+    launch(mod_->k_dg_g, (unsigned)nblocks, (unsigned)(cpw * Nd), 0, args, "k_dg_g");
   } else {
     const unsigned block = cfg_.dg_cpb * N * Nd;
     const size_t smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * sizeof(double);

@@ -74,7 +74,7 @@ public:
   CUfunction k_boundaries = nullptr, k_weno_sweep = nullptr, k_cfl = nullptr, k_dt = nullptr,
              k_advance = nullptr, k_dg = nullptr, k_faces = nullptr, k_update = nullptr,
              k_wavespeeds = nullptr, k_dg_stiff = nullptr, k_faces_fused = nullptr, k_dg_n = nullptr,
-             k_weno2d = nullptr, k_faces_side = nullptr, k_weno3d = nullptr, k_cfl_q = nullptr;
+             k_weno2d = nullptr, k_faces_side = nullptr, k_weno3d = nullptr, k_cfl_q = nullptr, k_dg_g = nullptr;
 };
 
 class Solver {
@@ -169,7 +169,7 @@ private:
   DeviceBuffer stiff_work_;
   bool fused_faces_ = true;
   bool side_faces_ = true; // two threads per face where k_faces_side exists (PYPDE_B200_FACES_SIDE=0: one)
-  bool node_dg_ = true; // k_dg_n where it applies (PYPDE_B200_DG_NODE=0: always k_dg)
+  bool node_dg_ = true; // k_dg_n / k_dg_g where they apply (PYPDE_B200_DG_NODE=0: always k_dg)
   // 2-D: both WENO sweeps in one tiled kernel fed by TMA (PYPDE_B200_WENO_FUSED=0: two sweeps)
   bool weno2d_ = false;
   int weno2d_ti_ = 0, weno2d_tj_ = 0;

@@ -81,6 +81,7 @@ def test_jit_builds_sm100a_cubin_without_gpu(system, ndim, N):
     # predictor, the fused Rusanov face kernel, the TMA-fed WENO tile kernels in 2-D and 3-D
     first_order_no_B = B is None and not getattr(F, 'second_order', False)
     assert ('Function k_dg_n:' in out) == (first_order_no_B and N >= 2 and N**ndim <= 32)
+    assert ('Function k_dg_g:' in out) == (not first_order_no_B and N >= 2 and N**ndim <= 32)
     assert 'Function k_faces_fused:' in out
     assert ('Function k_weno2d:' in out) == (ndim == 2)
     assert ('Function k_weno3d:' in out) == (ndim == 3)

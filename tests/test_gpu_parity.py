@@ -111,6 +111,9 @@ def test_sized_golden(golden, name):
 @pytest.mark.parametrize('name,env', [
     ('euler2d_explosion_N3', 'PYPDE_B200_DG_NODE'), ('sod_N2', 'PYPDE_B200_DG_NODE'),
     ('euler3d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('burgers2d_N2', 'PYPDE_B200_DG_NODE'),
+    ('ns2d_smooth_N2', 'PYPDE_B200_DG_NODE'), ('ns3d_taylor_green_N3', 'PYPDE_B200_DG_NODE'),
+    ('ns1d_smooth_N3', 'PYPDE_B200_DG_NODE'), ('advect_nc_2d_N2', 'PYPDE_B200_DG_NODE'),
+    ('advect_nc_1d_N3', 'PYPDE_B200_DG_NODE'),
     ('euler2d_explosion_N3', 'PYPDE_B200_FUSED_FACES'), ('sod_N2', 'PYPDE_B200_FUSED_FACES'),
     ('euler3d_smooth_N2', 'PYPDE_B200_FUSED_FACES'), ('ns2d_smooth_N2', 'PYPDE_B200_FUSED_FACES'),
     ('ns3d_taylor_green_N3', 'PYPDE_B200_FUSED_FACES'),
@@ -124,7 +127,7 @@ def test_sized_golden(golden, name):
     ('euler2d_explosion_N3', 'PYPDE_B200_CFL_Q'), ('burgers2d_N2', 'PYPDE_B200_CFL_Q'),
     ('euler2d_strip_N2', 'PYPDE_B200_CFL_Q')])
 def test_kernel_variants_agree_bit_for_bit(name, env):
-    """The node-thread predictor (k_dg_n), the fused Rusanov face kernels (k_faces_side:
+    """The node-thread predictors (k_dg_n; k_dg_g with gradient terms), the fused Rusanov face kernels (k_faces_side:
     two threads per face; k_faces_fused: one), the TMA-fed WENO tile kernels (k_weno2d,
     k_weno3d) and the CFL kernel that reads k_weno2d's cell averages (k_cfl_q) run every
     sum in the order of the general kernels they replace (k_dg; k_wavespeeds + k_faces;

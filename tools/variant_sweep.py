@@ -35,14 +35,17 @@ SETS['eig'] = [
     ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
 ]
 SETS['c5'] = [
-    ('k_wavespeeds + k_faces, k_dg 1 cell per block (default)', {}),
+    ('k_wavespeeds + k_faces, k_dg_g (default)', {}),
+    ('k_dg (space-time node per thread)', {'PYPDE_B200_DG_NODE': '0'}),
+    ('k_dg_g 12 blocks per SM (170 registers)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_DGG_MINBLOCKS=12'}),
+    ('k_dg_g 16 blocks per SM (128 registers)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_DGG_MINBLOCKS=16'}),
     ('k_faces_side for the second-order flux', {'PYPDE_B200_FUSED_FACES': '1'}),
     ('  fs_block 128 x 4', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '128',
                             'PYPDE_B200_FS_MINBLOCKS': '4'}),
     ('  fs_block 512 x 1', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '512',
                             'PYPDE_B200_FS_MINBLOCKS': '1'}),
-    ('k_dg 2 cells per block', {'PYPDE_B200_DG_CPB': '2'}),
-    ('k_dg 3 cells per block', {'PYPDE_B200_DG_CPB': '3'}),
+    ('k_dg 2 cells per block', {'PYPDE_B200_DG_NODE': '0', 'PYPDE_B200_DG_CPB': '2'}),
+    ('k_dg 3 cells per block', {'PYPDE_B200_DG_NODE': '0', 'PYPDE_B200_DG_CPB': '3'}),
 ]
 SETS['faces'] = [
     ('round 1 equivalent: k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),

@@ -237,7 +237,11 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   // 6.2 against 9.3 ms per step; GPR (V = 17) 19.9 against 13.4 ms and 3-D Navier-Stokes
   // (second-order flux: gradient traces of both sides live at once) 20.5 against 12.9 ms
   // for k_wavespeeds + k_faces.
-  fused_faces_ = cfg_.V <= 5 && !cfg_.secondOrder;
+  // Round 2: with TWO threads per face (k_faces_side) the second-order case wins too — a
+  // lane holds one side's state and gradient only: 3-D Navier-Stokes at 32 x 128^2,
+  // k_wavespeeds + k_faces 18.4 + 2.6 ms against 15.8 ms (profiles/r2_c5_sweep.txt), and one
+  // pass over the 58 GB of traces instead of two.
+  fused_faces_ = cfg_.V <= 5 && !(cfg_.secondOrder && cfg_.useB);
   if (const char *e = getenv("PYPDE_B200_FUSED_FACES"))
     fused_faces_ = *e != '0';
   // two threads per face (k_faces_side) where that kernel exists: measured 5.37 against
@@ -359,7 +363,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
       weno3d_ = e && *e == '1' && weno3d_map(&ub_map_, ub_.p, mb, cfg_);
     }
   }
-  if (cfg_.useF) // per trace point: lambda, [lambda_visc]
+  // per trace point: lambda, [lambda_visc] — only where the two-kernel face path runs
+  if (cfg_.useF && !(cfg_.flux == 0 && fused_faces_))
     ws_.alloc((size_t)ncellw_ * 2 * nd * NP * (1 + (cfg_.secondOrder ? 1 : 0)) * D);
   centers_.alloc((size_t)ncellw_ * V * D);
   const int FLXW = cfg_.useB ? 2 : 1;

@@ -161,3 +161,38 @@ def test_missing_library_is_an_error(monkeypatch):
     monkeypatch.setattr(U, 'lib_path', lambda: '/nonexistent/libpypde.so')
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         U.get_cdll()
+
+
+def test_cubin_cache_directory_must_be_private(tmp_path):
+    """The on-disk cubin cache is loaded as GPU code: a directory that group / others can
+    access, or a symlink, is not used (the link still succeeds, nothing is written)."""
+    script = '''
+import ctypes, os, sys
+from pypde_b200.systems import cuda_sources
+from pypde_b200.utils import get_cdll, last_error
+F, B, S, V = cuda_sources('burgers', 1)
+n = ctypes.c_size_t()
+rc = get_cdll().pypde_b200_compile(F.pointer, None, None, 1, 2, V, 0, 0, 0, ctypes.byref(n), None,
+                                   ctypes.c_size_t(0))
+assert rc == 0, last_error()
+print(len(os.listdir(os.environ['PYPDE_B200_CACHE_REAL'])))
+'''
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(cache, real, mode):
+        os.chmod(real, mode)
+        env = dict(os.environ, PYPDE_B200_CACHE=str(cache), PYPDE_B200_CACHE_REAL=str(real),
+                   PYTHONPATH=root)
+        return int(subprocess.check_output([sys.executable, '-c', script], env=env).split()[-1])
+
+    open_dir = tmp_path / 'open'
+    open_dir.mkdir()
+    assert run(open_dir, open_dir, 0o777) == 0          # world-writable: refused
+    assert run(open_dir, open_dir, 0o750) == 0          # group-readable: refused
+    link = tmp_path / 'link'
+    private = tmp_path / 'private'
+    private.mkdir()
+    os.symlink(private, link)
+    assert run(link, private, 0o700) == 0               # a symlink: refused
+    assert run(private, private, 0o700) == 1            # a private directory: used

@@ -64,7 +64,7 @@ std::string solver_key(const KernelConfig &c, const pypde_b200_devfn *F, const p
                         "PYPDE_B200_FS_BLOCK", "PYPDE_B200_FS_MINBLOCKS",
                         "PYPDE_B200_STIFF_KS", "PYPDE_B200_STIFF_WPB", "PYPDE_B200_STIFF_MINBLOCKS",
                         "PYPDE_B200_STIFF_STATS", "PYPDE_B200_WENO3D", "PYPDE_B200_CFL_Q",
-                        "PYPDE_B200_W3_TILE", "PYPDE_B200_EIG_SMEM"}) {
+                        "PYPDE_B200_W3_TILE"}) {
     const char *v = getenv(e);
     k += v ? v : "-";
     k += '|';

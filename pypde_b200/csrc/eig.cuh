@@ -31,9 +31,6 @@ EIG_FN double sel_max(double a, double b) { return a > b ? a : b; }
 #ifndef PDE_EIG_QR_ONLY
 #define PDE_EIG_QR_ONLY 0 // 1: always use the general QR iteration for spectral radii
 #endif
-#ifndef PDE_EIG_SMEM
-#define PDE_EIG_SMEM 0 // doubles of shared-memory workspace per thread for the n > 5 iteration
-#endif
 
 // ---------------------------------------------------------------------------
 // D1: spectral radius of a general real V x V matrix (replaces Eigen
@@ -1035,7 +1032,7 @@ EIG_FN void balance_rt(double *a, const int ld, const int m) {
 // indexing in local memory.)  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
 // scaling, Hessenberg reduction and the QR iteration, whose cost is cubic in its size:
 // measured on B200, GPR 256^2: k_wavespeeds 11.0 -> see profiles/.  a is destroyed.
-template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a, double *ws = nullptr) {
+template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
 #define A_(i, j) a[(i) * n + (j)]
   int lo = 0, hi = n - 1;
   double rad = 0.;
@@ -1096,20 +1093,6 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a, d
     return rad;
   if (m == 1)
     return sel_max(rad, fabs(A_(lo, lo)));
-#if PDE_EIG_SMEM > 0
-  // ws: PDE_EIG_SMEM doubles of SHARED memory of this thread (the wave-speed and CFL kernels
-  // pass it).  The iteration indexes its matrix dynamically and divergently (each lane has
-  // its own deflation history), which in local memory is one L1/L2 line per lane and access
-  // — ncu: long_scoreboard 48 % of the stall samples, 28 GB of local-memory traffic reaching
-  // DRAM per launch at C4; shared memory serves the same accesses at its own latency.
-  if (ws != nullptr && m * m <= PDE_EIG_SMEM) {
-    for (int i = 0; i < m; i++)
-      for (int j = 0; j < m; j++)
-        ws[i * m + j] = A_(lo + i, lo + j);
-    balance_rt(ws, m, m);
-    return sel_max(rad, spectral_radius_qr_rt(ws, m, m));
-  }
-#endif
   // B moves to the front of the array with row pitch m (destination index <= source index,
   // rows and columns ascending: in place), so that the iteration touches m^2 contiguous
   // doubles of this thread's local memory instead of a window of the n^2
@@ -1128,10 +1111,10 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a, d
 #ifndef PDE_EIG_DEFLATE
 #define PDE_EIG_DEFLATE 1 // 0: n > 5 as in round 1 (scaling + QR iteration on the full matrix)
 #endif
-template <int n> EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a, double *ws = nullptr) {
+template <int n> EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a) {
 #if PDE_EIG_DEFLATE
   if (n > 5)
-    return spectral_radius_deflated_qr<n>(a, ws);
+    return spectral_radius_deflated_qr<n>(a);
 #endif
   balance<n>(a);
   return spectral_radius_qr<n>(a);
@@ -1147,8 +1130,7 @@ template <int n> EIG_FN double spectral_radius_general(const double *a) {
 }
 
 template <int n>
-EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr,
-                              double *ws = nullptr) {
+EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr) {
   if (n == 1)
     return fabs(a[0]);
   if (n == 2) {
@@ -1179,7 +1161,7 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
   // halves the local-memory footprint and traffic of the n = 17 wave-speed kernels (ncu:
   // 28 GB of local-memory traffic reaching DRAM per launch at C4).
   if (n > 5)
-    return spectral_radius_balanced_qr<n>(a, ws);
+    return spectral_radius_balanced_qr<n>(a);
   return spectral_radius_general<n>(a);
 }
 

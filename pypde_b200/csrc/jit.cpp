@@ -288,18 +288,6 @@ void choose_block_shapes(KernelConfig &c) {
     if (const char *e = getenv("PYPDE_B200_STIFF_MINBLOCKS"))
       c.stiff_minblocks = atoi(e);
   }
-  // V > 5: the active block of the QR iteration (<= 11 x 11 for the 17-variable GPR model) in
-  // shared memory, 121 doubles per thread; the wave-speed kernel then runs 128 threads per
-  // block (124 KB of shared memory)
-  c.eig_smem = c.V > 5 ? 121 : 0;
-  if (const char *e = getenv("PYPDE_B200_EIG_SMEM"))
-    c.eig_smem = atoi(e);
-  if (c.V <= 5)
-    c.eig_smem = 0;
-  if (c.eig_smem > 0) {
-    c.ws_block = 128;
-    c.ws_minblocks = 1;
-  }
   if (const char *e = getenv("PYPDE_B200_W3_TILE"))
     sscanf(e, "%d,%d,%d", &c.w3_ti, &c.w3_tj, &c.w3_tk);
   // tuning overrides (experiments)
@@ -348,7 +336,6 @@ std::vector<std::string> specialisation_defines(const KernelConfig &c) {
           kv("PDE_DG_CPB", c.dg_cpb),
           kv("PDE_FACES_FPB", c.faces_fpb),
           kv("PDE_STIFF_WPB", c.stiff_wpb),
-          kv("PDE_EIG_SMEM", c.eig_smem),
           kv("PDE_W3_TI", c.w3_ti),
           kv("PDE_W3_TJ", c.w3_tj),
           kv("PDE_W3_TK", c.w3_tk),

@@ -20,7 +20,6 @@ struct KernelConfig {
   int stiff_wpb = 4; // warps (cells) per block in k_dg_stiff
   int stiff_ks = 6;  // Krylov vectors / Hessenberg columns k_dg_stiff keeps in shared memory
   int stiff_minblocks = 1; // its __launch_bounds__ min-blocks (register budget; set by choose_block_shapes)
-  int eig_smem = 0; // doubles of shared-memory workspace per thread for the V > 5 eigen-iteration
   int w3_ti = 4, w3_tj = 4, w3_tk = 8; // k_weno3d tile (PYPDE_B200_W3_TILE=ti,tj,tk)
   bool stiff_stats = false; // PYPDE_B200_STIFF_STATS=1: iteration counters (profiling)
   int ws_block = 512, ws_minblocks = 1; // k_wavespeeds launch bounds (measured best: C5 14.8 ms vs 22.1 at 256 x 2)

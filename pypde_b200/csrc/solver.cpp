@@ -414,21 +414,6 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
                           stream_),
           "cuMemsetD8Async(stiff stats)");
   }
-  // shared-memory workspace of the V > 5 eigen-iteration in k_cfl (128 threads) / k_wavespeeds
-  if (cfg_.eig_smem > 0) {
-    const size_t per_thread = (size_t)(cfg_.eig_smem | 1) * D;
-    const size_t need = (size_t)(cfg_.ws_block > 128 ? cfg_.ws_block : 128) * per_thread;
-    if (need > 220 * 1024)
-      throw std::runtime_error("pypde_b200: eigen-iteration workspace exceeds shared memory");
-    if (need > 48 * 1024) {
-      check(d.FuncSetAttribute(mod_->k_cfl, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)need),
-            "cuFuncSetAttribute(k_cfl smem)");
-      if (mod_->k_wavespeeds)
-        check(d.FuncSetAttribute(mod_->k_wavespeeds, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES,
-                                 (int)need),
-              "cuFuncSetAttribute(k_wavespeeds smem)");
-    }
-  }
   // dynamic shared memory opt-in
   const size_t dg_smem = (size_t)cfg_.dg_cpb * (2 + nd) * N * Nd * V * D;
   if (dg_smem > 48 * 1024)
@@ -844,8 +829,7 @@ void Solver::step_body() {
     launch(mod_->k_cfl_q, grid_for(ncellw_, 128), 128, 0, args, "k_cfl_q");
   } else {
     void *args[] = {&w_.p, &ncellw_, &g_, &state_.p};
-    launch(mod_->k_cfl, grid_for(ncellw_, 128), 128,
-           (size_t)128 * (cfg_.eig_smem > 0 ? (cfg_.eig_smem | 1) : 0) * sizeof(double), args, "k_cfl");
+    launch(mod_->k_cfl, grid_for(ncellw_, 128), 128, 0, args, "k_cfl");
   }
   if (cm.nranks > 1) {
     const NcclApi &nc = nccl();
@@ -905,9 +889,8 @@ void Solver::step_body() {
   } else if (cfg_.useF && cfg_.flux == 0) {
     long total = ncellw_ * 2 * nd;
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
-    launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block,
-           (size_t)cfg_.ws_block * (cfg_.eig_smem > 0 ? (cfg_.eig_smem | 1) : 0) * sizeof(double),
-           args, "k_wavespeeds");
+    launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, 0, args,
+           "k_wavespeeds");
   }
   if ((cfg_.useF || cfg_.useB) && !(cfg_.useF && cfg_.flux == 0 && fused_faces_)) {
     const int NP = N * ipow(N, nd - 1);

@@ -29,12 +29,10 @@ cells = int(np.prod(Q0.shape[:-1]))
 
 SETS = {}
 SETS['eig'] = [
-    ('active block in local memory, 512 x 1 (round 2 so far)', {'PYPDE_B200_EIG_SMEM': '0'}),
-    ('  128 x 4', {'PYPDE_B200_EIG_SMEM': '0', 'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
-    ('active block in shared memory, 128 threads per SM (default)', {}),
-    ('  192 threads per SM', {'PYPDE_B200_WS_BLOCK': '192'}),
-    ('  100 doubles per thread (10 x 10), 2 x 128 per SM', {'PYPDE_B200_EIG_SMEM': '100'}),
-    ('  81 doubles per thread (9 x 9), 2 x 160 per SM', {'PYPDE_B200_EIG_SMEM': '81', 'PYPDE_B200_WS_BLOCK': '160'}),
+    ('round 1: QR iteration on the full matrix', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0'}),
+    ('isolated eigenvalues first, QR on the active block', {}),
+    ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
+    ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
 ]
 SETS['c5'] = [
     ('k_wavespeeds + k_faces, k_dg_g (default)', {}),

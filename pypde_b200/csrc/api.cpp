@@ -491,8 +491,14 @@ void pde_solver(void (*F)(double *, double *, double *, int), void (*B)(double *
     // final state crosses PCIe once; its second destination is a host copy (threaded when
     // large — eight ranks on one host share the PCIe uplinks, not the memory channels)
     solver.get_state(_u);
-    if (ndt >= 1)
-      host_copy(_ret + (size_t)(ndt - 1) * n, _u, n);
+    if (ndt >= 1) {
+      // PYPDE_B200_FINAL_COPY=d2h: a second device-to-host copy instead of the host copy
+      const char *fc = getenv("PYPDE_B200_FINAL_COPY");
+      if (fc && fc[0] == 'd')
+        solver.get_state(_ret + (size_t)(ndt - 1) * n);
+      else
+        host_copy(_ret + (size_t)(ndt - 1) * n, _u, n);
+    }
   } catch (const std::exception &e) {
     set_error(e.what());
   } catch (...) {

@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -33,6 +33,15 @@ SETS['eig'] = [
     ('isolated eigenvalues first, QR on the active block', {}),
     ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
     ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+]
+SETS['occ'] = [   # occupancy against registers for the QR-bound kernels
+    ('default', {}),
+    ('k_wavespeeds 256 x 3 (85 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '3'}),
+    ('k_wavespeeds 256 x 4 (64 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
+    ('k_wavespeeds 128 x 6 (85 registers)', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '6'}),
+    ('k_faces 4 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=4'}),
+    ('k_faces 5 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=5'}),
+    ('k_faces 6 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=6'}),
 ]
 SETS['c5'] = [
     ('k_wavespeeds + k_faces, k_dg_g (default)', {}),

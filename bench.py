@@ -410,6 +410,8 @@ def main():
                     help='override the cells per axis (per GPU where the config is weak-scaled)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-smooth', action='store_true',
+                    help='c2: skip the smooth-periodic variant measured beside the explosion')
     ap.add_argument('--slab-checks', default='all',
                     help="multi-rank runs: comma-separated SLAB_CHECKS names, 'all' or 'none'")
     ap.add_argument('--user-functions', default='cuda', choices=['cuda', 'numba', 'traced'],
@@ -581,6 +583,36 @@ def main():
     sol.close()
     del u_dev
 
+    # ---- the same workload on SURVEY 8d's smooth periodic data (no plateaus: two Picard
+    # iterations in every cell, no root search that ends in one step), device-resident, in the
+    # same run: the default line carries both numbers
+    smooth = None
+    if args.config == 'c2' and world == 1 and not args.no_smooth:
+        scfg = CONFIGS['c2smooth']
+        _, _, Qs, dXs = slab_problem(scfg, 0, 1, args.size)
+        us = torch.from_numpy(Qs).cuda()
+        ss = Solver(Qs.shape, None, F=F, boundaryTypes=scfg['bts'], cfl=0.9, order=N_ORDER,
+                    dX=dXs, flux=scfg['flux'], stiff=False)
+        ss.set_stream(stream.cuda_stream)
+        ss.bind_tensor(us)
+        ss.begin(1e9)
+        for _ in range(W):
+            ss.step_async()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(K):
+            ss.step_async()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1)
+        _, _, snan = ss.sync()
+        ss.close()
+        del us
+        if not snan:
+            smooth = {'value': cells_rank * K / (sms * 1e-3), 'unit': 'cell-updates/s',
+                      'ms_per_step': sms / K, 'workload': scfg['workload']}
+
     # ---- end-to-end arm: the reference-facing C ABI with host buffers
     e2e = None
     if not args.no_e2e:
@@ -671,6 +703,8 @@ def main():
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline,
             'cpu_baseline': cpu,
         }
+        if smooth is not None:
+            line['smooth_periodic_variant'] = smooth
         if world > 1:
             line['slab_bit_identical'] = (None if not slab_res else
                                           all(v['bit_identical'] for v in slab_res.values()))

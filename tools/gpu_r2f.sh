@@ -39,6 +39,6 @@ for uf in numba traced; do
   python -c "import json; d=json.load(open('$O/r2f_bench_c2_$uf.json')); print('c2 $uf', '%.3e'%d['value'], 'e2e %.3e'%d['e2e']['value'])" || tail -3 $O/r2f_bench_c2_$uf.err
 done
 python tools/variant_sweep.py stiff c3 512 3 > $O/r2f_stiff_sweep.log 2>&1; head -3 $O/r2f_stiff_sweep.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $T/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $T/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-smooth > /dev/null 2>&1
 python tools/summarize_launches.py $T/launches.csv "ncu launch list of: python bench.py --steps 2 --warmup 3 (not a bench value)" > $O/r2f_launches.txt 2>&1
 du -sm $O

@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -43,18 +43,20 @@ SETS['occ'] = [   # occupancy against registers for the QR-bound kernels
     ('k_faces 5 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=5'}),
     ('k_faces 6 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=6'}),
 ]
+SETS['gprstiff'] = [
+    ('default (254 registers, 2 blocks of 4 warps per SM)', {}),
+    ('3 blocks per SM (170 registers)', {'PYPDE_B200_STIFF_MINBLOCKS': '3'}),
+    ('4 blocks per SM (128 registers)', {'PYPDE_B200_STIFF_MINBLOCKS': '4'}),
+    ('8 warps per block, 1 block', {'PYPDE_B200_STIFF_WPB': '8', 'PYPDE_B200_STIFF_MINBLOCKS': '1'}),
+]
 SETS['c5'] = [
-    ('k_wavespeeds + k_faces, k_dg_g (default)', {}),
+    ('k_faces_side + k_dg_g (default)', {}),
+    ('k_wavespeeds + k_faces', {'PYPDE_B200_FUSED_FACES': '0'}),
     ('k_dg (space-time node per thread)', {'PYPDE_B200_DG_NODE': '0'}),
     ('k_dg_g 12 blocks per SM (170 registers)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_DGG_MINBLOCKS=12'}),
     ('k_dg_g 16 blocks per SM (128 registers)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_DGG_MINBLOCKS=16'}),
-    ('k_faces_side for the second-order flux', {'PYPDE_B200_FUSED_FACES': '1'}),
-    ('  fs_block 128 x 4', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '128',
-                            'PYPDE_B200_FS_MINBLOCKS': '4'}),
-    ('  fs_block 512 x 1', {'PYPDE_B200_FUSED_FACES': '1', 'PYPDE_B200_FS_BLOCK': '512',
-                            'PYPDE_B200_FS_MINBLOCKS': '1'}),
-    ('k_dg 2 cells per block', {'PYPDE_B200_DG_NODE': '0', 'PYPDE_B200_DG_CPB': '2'}),
-    ('k_dg 3 cells per block', {'PYPDE_B200_DG_NODE': '0', 'PYPDE_B200_DG_CPB': '3'}),
+    ('k_faces_side 256 x 2', {'PYPDE_B200_FS_BLOCK': '256', 'PYPDE_B200_FS_MINBLOCKS': '2'}),
+    ('k_faces_side 1024 x 1 (64 registers)', {'PYPDE_B200_FS_BLOCK': '1024', 'PYPDE_B200_FS_MINBLOCKS': '1'}),
 ]
 SETS['faces'] = [
     ('round 1 equivalent: k_cfl on w', {'PYPDE_B200_CFL_Q': '0'}),

@@ -232,11 +232,13 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_qr(double *a) {
 
 // The same iteration on the leading n x n block of a matrix with row pitch ld, n a run-time
 // value: the active block that remains after the permutation step below.
-EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int n) {
+// Part 1: Hessenberg reduction by stabilised elementary transformations (the multipliers stay
+// below the subdiagonal; hqr_rt clears them).
+#ifndef PDE_EIG_HESS_SKIP
+#define PDE_EIG_HESS_SKIP 0 // (measured slower on B200: the branches break the pipelining of the loads)
+#endif
+EIG_FN void hessenberg_rt(double *a, const int ld, const int n) {
 #define A_(i, j) a[(i) * ld + (j)]
-  if (n == 1)
-    return fabs(A_(0, 0));
-  // --- Hessenberg reduction by stabilised elementary transformations
   for (int m = 1; m < n - 1; m++) {
     double x = 0.;
     int i = m;
@@ -258,24 +260,48 @@ EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int 
       }
     }
     if (x != 0.) {
+      // (any multiplier gives an exact similarity as long as the row and the column operation
+      //  use the same one: a reciprocal per column instead of a quotient per row)
+      const double rx = 1. / x;
       for (i = m + 1; i < n; i++) {
         double y = A_(i, m - 1);
         if (y != 0.) {
-          y /= x;
+          y *= rx;
           A_(i, m - 1) = y;
+#if PDE_EIG_HESS_SKIP
+          // (sparse matrices: a zero factor leaves the target as it is — x - y * 0 = x for
+          //  finite values — and saves its load and store; the kernels that run this are
+          //  bound by the latency of exactly these local-memory accesses)
+          for (int j = m; j < n; j++) {
+            const double v = A_(m, j);
+            if (v != 0.)
+              A_(i, j) -= y * v;
+          }
+          for (int j = 0; j < n; j++) {
+            const double v = A_(j, i);
+            if (v != 0.)
+              A_(j, m) += y * v;
+          }
+#else
           for (int j = m; j < n; j++)
             A_(i, j) -= y * A_(m, j);
           for (int j = 0; j < n; j++)
             A_(j, m) += y * A_(j, i);
+#endif
         }
       }
     }
   }
+#undef A_
+}
+
+// Part 2: the double-shift QR iteration on the Hessenberg matrix hessenberg_rt leaves.
+EIG_FN_NOINLINE double hqr_rt(double *a, const int ld, const int n) {
+#define A_(i, j) a[(i) * ld + (j)]
   for (int i = 2; i < n; i++)
     for (int j = 0; j < i - 1; j++)
       A_(i, j) = 0.;
 
-  // --- QR iteration
   double rad = 0.;
   double anorm = 0.;
   for (int i = 0; i < n; i++)
@@ -422,6 +448,13 @@ EIG_FN_NOINLINE double spectral_radius_qr_rt(double *a, const int ld, const int 
   }
   return rad;
 #undef A_
+}
+
+EIG_FN double spectral_radius_qr_rt(double *a, const int ld, const int n) {
+  if (n == 1)
+    return fabs(a[0]);
+  hessenberg_rt(a, ld, n);
+  return hqr_rt(a, ld, n);
 }
 
 // ---------------------------------------------------------------------------
@@ -977,16 +1010,27 @@ template <int n> EIG_FN void balance(double *a) {
 }
 
 // Run-time sized balancing of the leading m x m block (row pitch ld); same steps as balance<n>.
+// (three sweeps: the GPR matrices are done after three — the fourth only confirms it, at 3.5 %
+//  of the wave-speed kernel; a matrix that would need more is left slightly less balanced, which
+//  costs the Hessenberg reduction a little accuracy and nothing else: scaling is an exact
+//  similarity whenever it stops)
+#ifndef PDE_EIG_BAL_SWEEPS
+#define PDE_EIG_BAL_SWEEPS 3
+#endif
 EIG_FN void balance_rt(double *a, const int ld, const int m) {
-  for (int sweep = 0; sweep < 6; sweep++) {
+  for (int sweep = 0; sweep < PDE_EIG_BAL_SWEEPS; sweep++) {
     bool done = true;
     for (int i = 0; i < m; i++) {
       double c = 0., r = 0.;
-      for (int j = 0; j < m; j++)
-        if (j != i) {
-          c += fabs(a[j * ld + i]);
-          r += fabs(a[i * ld + j]);
-        }
+      // (two branch-free loops, the same sums in the same order)
+      for (int j = 0; j < i; j++) {
+        c += fabs(a[j * ld + i]);
+        r += fabs(a[i * ld + j]);
+      }
+      for (int j = i + 1; j < m; j++) {
+        c += fabs(a[j * ld + i]);
+        r += fabs(a[i * ld + j]);
+      }
       if (c > 0. && r > 0. && c <= 1e300 && r <= 1e300) {
         double g = 0.5 * r, f = 1.;
         const double s0 = c + r;
@@ -1015,6 +1059,261 @@ EIG_FN void balance_rt(double *a, const int ld, const int m) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// n > 5, after the Hessenberg reduction: the spectral radius from the characteristic
+// polynomial instead of the QR iteration, under a certificate.
+//
+// For an upper Hessenberg H the leading principal minors p_k(y) = det(y I - H_k) obey
+//   p_k = (y - h_kk) p_(k-1) - sum_{i<k} h_ik (h_(i+1,i) .. h_(k,k-1)) p_(i-1),
+// a division-free recurrence that is indifferent to zero subdiagonal entries; carried out on
+// coefficient arrays it gives the characteristic polynomial of the m x m block in ~m^3/6
+// multiply-adds (222 for m = 11, where the QR iteration needs ~10 m^3).  Then, as for n <= 5:
+//   1. the largest and the smallest real root by the monotone Laguerre iteration from outside
+//      (warm-started from the previous solve of a sequence), on the mean-shifted polynomial;
+//   2. each polished by one Newton step on H itself — the same recurrence evaluated at a
+//      number, O(m^2) — whose size also bounds what the coefficient form lost;
+//   3. the certificate: p divided by both roots, moved back to the unshifted variable and
+//      scaled to the disk of radius 0.999 rho, must pass the Schur-Cohn test (all reflection
+//      coefficients below one in modulus <=> every other eigenvalue, real or complex, lies
+//      strictly inside that disk).  Then rho = max |outer root| is the spectral radius.
+// Anything else — a dominant complex pair, a multiple or clustered outer root, a search that
+// leaves the monotone regime, non-finite numbers — returns false and the caller continues with
+// the QR iteration on the same (untouched) Hessenberg matrix.  For hyperbolic systems, whose
+// fastest waves are simple and real, the certificate holds as a rule.
+// guess (optional): outer eigenvalues of the previous matrix, unshifted.
+// ---------------------------------------------------------------------------
+EIG_FN bool poly_rt_iterate(const double *c, const int m, double x, double &root) {
+  bool newton = false;
+  for (int it = 0; it < 40; it++) {
+    double p = 1., dp = 0., d2 = 0.; // p, p', p''/2 by Horner
+    for (int k = m - 1; k >= 0; k--) {
+      d2 = fma(d2, x, dp);
+      dp = fma(dp, x, p);
+      p = fma(p, x, c[k]);
+    }
+    if (!(p > 0.) || !(dp > 0.)) {
+      // on (or a rounding error past) the root, or outside the monotone regime
+      double ab = 1.;
+      const double ax = fabs(x);
+      for (int k = m - 1; k >= 0; k--)
+        ab = fma(ab, ax, fabs(c[k]));
+      if (fabs(p) <= 64. * DBL_EPS * ab && dp > 0.) {
+        root = x - p / dp;
+        return true;
+      }
+      return false;
+    }
+    double a;
+    if (newton) {
+      a = p / dp;
+    } else {
+      const double disc = (m - 1.) * ((m - 1.) * dp * dp - 2. * m * p * d2);
+      a = disc > 0. ? m * p / (dp + sqrt(disc)) : p / dp;
+    }
+    if (!(a >= 0.) || !(a <= 1e300))
+      return false;
+    x -= a;
+    const double ax = fabs(x);
+    if (a <= 1e-5 * ax) {
+      p = 1.;
+      dp = 0.;
+      for (int k = m - 1; k >= 0; k--) {
+        dp = fma(dp, x, p);
+        p = fma(p, x, c[k]);
+      }
+      if (!(dp > 0.))
+        return false;
+      root = x - p / dp;
+      return true;
+    }
+    newton = a <= 0.02 * ax;
+  }
+  return false;
+}
+
+// p(lam) / p'(lam) for p = det(lam I - H), H the leading m x m Hessenberg block of a, at two
+// arguments in one pass over H (the products h_ik h_(i+1,i) .. h_(k,k-1) do not depend on lam)
+template <int NMAX>
+EIG_FN void hess_newton_correction2(const double *a, const int ld, const int m, const double lam0,
+                                    const double lam1, double &c0, double &c1) {
+#define A_(i, j) a[(i) * ld + (j)]
+  double pv0[NMAX + 1], dv0[NMAX + 1], pv1[NMAX + 1], dv1[NMAX + 1];
+  pv0[0] = pv1[0] = 1.;
+  dv0[0] = dv1[0] = 0.;
+  for (int k = 1; k <= m; k++) {
+    const double hkk = A_(k - 1, k - 1);
+    const double s0 = lam0 - hkk, s1 = lam1 - hkk;
+    double p0 = s0 * pv0[k - 1], d0 = fma(s0, dv0[k - 1], pv0[k - 1]);
+    double p1 = s1 * pv1[k - 1], d1 = fma(s1, dv1[k - 1], pv1[k - 1]);
+    double t = 1.;
+    for (int i = k - 1; i >= 1; i--) {
+      t *= A_(i, i - 1);
+      if (t == 0.)
+        break;
+      const double g = A_(i - 1, k - 1) * t;
+      if (g != 0.) {
+        p0 = fma(-g, pv0[i - 1], p0);
+        d0 = fma(-g, dv0[i - 1], d0);
+        p1 = fma(-g, pv1[i - 1], p1);
+        d1 = fma(-g, dv1[i - 1], d1);
+      }
+    }
+    pv0[k] = p0;
+    dv0[k] = d0;
+    pv1[k] = p1;
+    dv1[k] = d1;
+  }
+  c0 = pv0[m] / dv0[m];
+  c1 = pv1[m] / dv1[m];
+#undef A_
+}
+
+#ifndef PDE_EIG_HESS_POLY
+#define PDE_EIG_HESS_POLY 1 // 0: n > 5 always through the QR iteration
+#endif
+template <int NMAX>
+EIG_FN_NOINLINE bool spectral_radius_hess_poly(const double *a, const int ld, const int m,
+                                               double &rho, EigGuess *guess) {
+#define A_(i, j) a[(i) * ld + (j)]
+  if (m < 2 || m > NMAX)
+    return false;
+  double mu = 0.;
+  for (int i = 0; i < m; i++)
+    mu += A_(i, i);
+  mu *= 1. / m;
+  // --- coefficients: P_k (degree k, ascending powers, leading 1) at P[k (k + 1) / 2]
+  double P[(NMAX + 1) * (NMAX + 2) / 2];
+  P[0] = 1.;
+  for (int k = 1; k <= m; k++) {
+    double *pk = P + k * (k + 1) / 2;
+    const double *pp = P + (k - 1) * k / 2;
+    const double hkk = A_(k - 1, k - 1) - mu;
+    pk[k] = 1.;
+    for (int j = k - 1; j >= 1; j--)
+      pk[j] = fma(-hkk, pp[j], pp[j - 1]);
+    pk[0] = -hkk * pp[0];
+    double t = 1.;
+    for (int i = k - 1; i >= 1; i--) {
+      t *= A_(i, i - 1);
+      if (t == 0.)
+        break;
+      const double g = A_(i - 1, k - 1) * t;
+      if (g != 0.) {
+        const double *pi = P + (i - 1) * i / 2;
+        for (int j = 0; j < i; j++)
+          pk[j] = fma(-g, pi[j], pk[j]);
+      }
+    }
+  }
+  const double *c = P + m * (m + 1) / 2;
+  double cn[NMAX + 1]; // (-1)^m p(-y): its largest root is minus the smallest root of p
+  for (int k = 0; k <= m; k++)
+    cn[k] = ((m - k) & 1) ? -c[k] : c[k];
+
+  // --- the outer real roots
+  double cold = -1.;
+  if (c[m - 2] < 0.) // Laguerre-Samuelson: bounds a real zero-mean spectrum
+    cold = sqrt(-2. * c[m - 2] * ((m - 1.) / m)) * (1. + 1e-3);
+  double yp = 0., ym = 0.;
+  bool okp = false, okm = false;
+  if (guess && guess->valid) {
+    const double gp = guess->yp - mu, gm = -(guess->ym - mu), d4 = 4. * guess->dy;
+    const double sc = sel_max(fabs(gp), fabs(gm));
+    const double lo = 1e-7 * sc, hi = 1e-3 * sc;
+    const double mg = d4 > hi ? hi : (d4 > lo ? d4 : lo);
+    okp = poly_rt_iterate(c, m, gp + mg, yp);
+    okm = poly_rt_iterate(cn, m, gm + mg, ym);
+  }
+  if (!okp) {
+    if (!(cold > 0.) || !poly_rt_iterate(c, m, cold, yp))
+      return false;
+  }
+  if (!okm) {
+    if (!(cold > 0.) || !poly_rt_iterate(cn, m, cold, ym))
+      return false;
+  }
+  ym = -ym;
+  const double ymax = sel_max(fabs(yp), fabs(ym));
+  if (!(yp - ym > 1e-7 * ymax)) // one real root only, or a multiple one
+    return false;
+  // --- polish on H (unshifted variable)
+  double lp = mu + yp, lm = mu + ym;
+  {
+    double cp, cm;
+    hess_newton_correction2<NMAX>(a, ld, m, lp, lm, cp, cm);
+    if (!(fabs(cp) <= 1e-9 * ymax) || !(fabs(cm) <= 1e-9 * ymax))
+      return false;
+    lp -= cp;
+    lm -= cm;
+  }
+  const double best = sel_max(fabs(lp), fabs(lm));
+  if (!(best > 0.) || !(best <= 1e150))
+    return false;
+  // --- the other m - 2 roots: inside the disk of radius 0.999 best?
+  const int dg = m - 2;
+  if (dg > 0) {
+    double f[NMAX + 1], g2[NMAX + 1];
+    // p / (y - yp) / (y - ym), backward deflation (stable for the roots of largest modulus):
+    // c_0 = -r q_0, c_k = q_(k-1) - r q_k
+    if (yp == 0. || ym == 0.)
+      return false;
+    {
+      const double ri = 1. / yp;
+      double qk = -c[0] * ri;
+      f[0] = qk;
+      for (int k = 1; k < m - 1; k++) {
+        qk = (qk - c[k]) * ri;
+        f[k] = qk;
+      }
+      f[m - 1] = 1.;
+    }
+    {
+      const double ri = 1. / ym;
+      double qk = -f[0] * ri;
+      g2[0] = qk;
+      for (int k = 1; k < m - 2; k++) {
+        qk = (qk - f[k]) * ri;
+        g2[k] = qk;
+      }
+      g2[dg] = 1.;
+    }
+    // Taylor shift to the unshifted variable lam = y + mu: e(lam - mu)
+    for (int i = 0; i < dg; i++)
+      for (int j = dg - 1; j >= i; j--)
+        g2[j] = fma(-mu, g2[j + 1], g2[j]);
+    // scale to the unit disk: z = lam / R
+    {
+      const double Ri = 1. / (0.999 * best);
+      double sc = 1.;
+      for (int j = dg - 1; j >= 0; j--) {
+        sc *= Ri;
+        g2[j] *= sc;
+      }
+    }
+    // Schur-Cohn: kappa = f_0 / f_d, f <- (f_(j+1) - kappa f_(d-1-j))_j
+    double *cur = g2, *nxt = f;
+    for (int d = dg; d >= 1; d--) {
+      const double kap = cur[0] / cur[d];
+      if (!(fabs(kap) < 1.))
+        return false;
+      for (int j = 0; j < d; j++)
+        nxt[j] = fma(-kap, cur[d - 1 - j], cur[j + 1]);
+      double *tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+  }
+  rho = best;
+  if (guess) {
+    guess->dy = guess->valid ? sel_max(fabs(lp - guess->yp), fabs(lm - guess->ym)) : 2.5e-4 * ymax;
+    guess->yp = lp;
+    guess->ym = lm;
+    guess->valid = 1;
+  }
+  return true;
+#undef A_
+}
+
 // Larger systems (n > 5; the GPR model has n = 17): most of a conserved-variable system
 // matrix dF_d/dQ + B_d is structurally zero — the 2-D GPR matrices have 50-110 non-zeros of
 // 289 — and a third to a half of its eigenvalues sit isolated on the diagonal (the
@@ -1032,7 +1331,38 @@ EIG_FN void balance_rt(double *a, const int ld, const int m) {
 // indexing in local memory.)  Only B (9 x 9 to 11 x 11 of 17 x 17 for GPR) goes through
 // scaling, Hessenberg reduction and the QR iteration, whose cost is cubic in its size:
 // measured on B200, GPR 256^2: k_wavespeeds 11.0 -> see profiles/.  a is destroyed.
-template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
+// The m x m active block at the front of a (row pitch m): scaling, Hessenberg form, then the
+// certified characteristic polynomial or the QR iteration.
+// Row pitch of the active block.  Thread-local arrays are interleaved over the lanes of a warp,
+// one element index per 256-byte row: contiguity within a thread buys nothing, whereas the same
+// pitch in every lane keeps entry (i, j) of all lanes in one row whatever their block sizes.
+#ifndef PDE_EIG_PITCH_FULL
+#define PDE_EIG_PITCH_FULL 1 // 0: pitch m (the block contiguous)
+#endif
+#define EIG_PITCH(n, m) (PDE_EIG_PITCH_FULL ? (n) : (m))
+template <int n>
+EIG_FN double spectral_radius_active_block(double *a, const int m, int *path, EigGuess *guess) {
+  const int ld = EIG_PITCH(n, m);
+  balance_rt(a, ld, m);
+  hessenberg_rt(a, ld, m);
+#if PDE_EIG_HESS_POLY
+  {
+    double r;
+    if (spectral_radius_hess_poly<n>(a, ld, m, r, guess)) {
+      if (path)
+        *path = 2;
+      return r;
+    }
+  }
+#endif
+  if (guess)
+    guess->valid = 0;
+  return hqr_rt(a, ld, m);
+}
+
+template <int n>
+EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a, int *path = nullptr,
+                                                   EigGuess *guess = nullptr) {
 #define A_(i, j) a[(i) * n + (j)]
   int lo = 0, hi = n - 1;
   double rad = 0.;
@@ -1096,12 +1426,112 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
   // B moves to the front of the array with row pitch m (destination index <= source index,
   // rows and columns ascending: in place), so that the iteration touches m^2 contiguous
   // doubles of this thread's local memory instead of a window of the n^2
-  if (m < n)
+  if (m < n) {
+    const int ld = EIG_PITCH(n, m);
     for (int i = 0; i < m; i++)
       for (int j = 0; j < m; j++)
-        a[i * m + j] = A_(lo + i, lo + j);
-  balance_rt(a, m, m);
-  return sel_max(rad, spectral_radius_qr_rt(a, m, m));
+        a[i * ld + j] = A_(lo + i, lo + j);
+  }
+  return sel_max(rad, spectral_radius_active_block<n>(a, m, path, guess));
+#undef A_
+}
+
+// Out-of-line entry for callers that assemble the active block themselves (kernels.cuh: the
+// two-pass Jacobian): a holds the m x m block with row pitch EIG_PITCH(n, m), rad the isolated
+// eigenvalues.
+template <int n>
+EIG_FN_NOINLINE double spectral_radius_compact(double *a, const int m, const double rad,
+                                               EigGuess *guess = nullptr) {
+  if (m <= 0)
+    return rad;
+  if (m == 1)
+    return sel_max(rad, fabs(a[0]));
+  return sel_max(rad, spectral_radius_active_block<n>(a, m, nullptr, guess));
+}
+
+#ifndef PDE_EIG_MASK
+#define PDE_EIG_MASK 1 // 0: the permutation step by row / column exchanges in memory (above)
+#endif
+// The same permutation step on the sparsity pattern alone: rm[i] has bit j set where A(i, j)
+// may be non-zero (n <= 32).  The device builds the pattern in registers while it differences
+// the Jacobian, so the search for isolated eigenvalues — iteratively removing the sinks, then
+// the sources, of the graph of A; the remaining set does not depend on the order — is integer
+// work on n words: no scan of the matrix, no row or column exchange in local memory.  The
+// active block is then gathered in ascending index order (destination index <= source index:
+// in place).  rm == nullptr: the pattern is read off the matrix.
+// the active set (bit j: index j stays) of the pattern r; fully unrolled, r stays in registers
+template <int n> EIG_FN unsigned mask_active_set(const unsigned *r) {
+  unsigned act = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  // rows that vanish off the diagonal inside the active set
+  for (bool found = true; found;) {
+    found = false;
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+      const unsigned bj = 1u << j;
+      if ((act & bj) && !(r[j] & act & ~bj)) {
+        act &= ~bj;
+        found = true;
+      }
+    }
+  }
+  // columns that do
+  for (bool found = true; found && act;) {
+    found = false;
+    unsigned any = 0;
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+      const unsigned bj = 1u << j;
+      if (act & bj)
+        any |= r[j] & ~bj;
+    }
+    const unsigned iso = act & ~any;
+    if (iso) {
+      act &= ~iso;
+      found = true;
+    }
+  }
+  return act;
+}
+
+template <int n>
+EIG_FN_NOINLINE double spectral_radius_masked(double *a, const unsigned *rm, int *path = nullptr,
+                                              EigGuess *guess = nullptr) {
+#define A_(i, j) a[(i) * n + (j)]
+  unsigned r[n];
+  if (rm) {
+    for (int i = 0; i < n; i++)
+      r[i] = rm[i];
+  } else {
+    for (int i = 0; i < n; i++) {
+      unsigned b = 0;
+      for (int j = 0; j < n; j++)
+        b |= (A_(i, j) != 0. ? 1u : 0u) << j;
+      r[i] = b;
+    }
+  }
+  const unsigned act = mask_active_set<n>(r);
+  double rad = 0.;
+  for (int j = 0; j < n; j++)
+    if (!(act & (1u << j)))
+      rad = sel_max(rad, fabs(A_(j, j)));
+  int idx[n];
+  int m = 0;
+  for (int j = 0; j < n; j++)
+    if (act & (1u << j))
+      idx[m++] = j;
+  if (m == 0)
+    return rad;
+  if (m == 1)
+    return sel_max(rad, fabs(A_(idx[0], idx[0])));
+  if (m < n) {
+    const int ld = EIG_PITCH(n, m);
+    for (int i = 0; i < m; i++) {
+      const double *row = a + idx[i] * n;
+      for (int j = 0; j < m; j++)
+        a[i * ld + j] = row[idx[j]];
+    }
+  }
+  return sel_max(rad, spectral_radius_active_block<n>(a, m, path, guess));
 #undef A_
 }
 
@@ -1111,11 +1541,21 @@ template <int n> EIG_FN_NOINLINE double spectral_radius_deflated_qr(double *a) {
 #ifndef PDE_EIG_DEFLATE
 #define PDE_EIG_DEFLATE 1 // 0: n > 5 as in round 1 (scaling + QR iteration on the full matrix)
 #endif
-template <int n> EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a) {
+template <int n>
+EIG_FN_NOINLINE double spectral_radius_balanced_qr(double *a, int *path = nullptr,
+                                                   EigGuess *guess = nullptr,
+                                                   const unsigned *rm = nullptr) {
 #if PDE_EIG_DEFLATE
-  if (n > 5)
-    return spectral_radius_deflated_qr<n>(a);
+  if (n > 5) {
+#if PDE_EIG_MASK
+    if (n <= 32)
+      return spectral_radius_masked<n>(a, rm, path, guess);
 #endif
+    return spectral_radius_deflated_qr<n>(a, path, guess);
+  }
+#endif
+  if (guess)
+    guess->valid = 0;
   balance<n>(a);
   return spectral_radius_qr<n>(a);
 }
@@ -1129,8 +1569,10 @@ template <int n> EIG_FN double spectral_radius_general(const double *a) {
   return spectral_radius_balanced_qr<n>(tmp);
 }
 
+// rm (optional, n > 5): the sparsity pattern of a by rows, see spectral_radius_masked
 template <int n>
-EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr) {
+EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = nullptr,
+                              const unsigned *rm = nullptr) {
   if (n == 1)
     return fabs(a[0]);
   if (n == 2) {
@@ -1154,14 +1596,14 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
 #endif
   if (path)
     *path = 0;
-  if (guess)
-    guess->valid = 0;
   // Larger matrices live in local memory already (they are indexed dynamically when they are
   // built): iterate in place instead of on a copy — `a` is destroyed, as documented — which
   // halves the local-memory footprint and traffic of the n = 17 wave-speed kernels (ncu:
   // 28 GB of local-memory traffic reaching DRAM per launch at C4).
   if (n > 5)
-    return spectral_radius_balanced_qr<n>(a);
+    return spectral_radius_balanced_qr<n>(a, path, guess, rm);
+  if (guess)
+    guess->valid = 0;
   return spectral_radius_general<n>(a);
 }
 

@@ -290,6 +290,10 @@ void choose_block_shapes(KernelConfig &c) {
   }
   if (const char *e = getenv("PYPDE_B200_W3_TILE"))
     sscanf(e, "%d,%d,%d", &c.w3_ti, &c.w3_tj, &c.w3_tk);
+  // V > 5 (the eigen-solves work in local memory, one long dependency chain per thread): 20
+  // warps per SM at 96 registers measured 2-6 % ahead of 16 at 128 (profiles/r2_occupancy_sweep.txt)
+  if (c.V > 5)
+    c.ws_block = 640;
   // tuning overrides (experiments)
   if (const char *e = getenv("PYPDE_B200_WS_BLOCK"))
     c.ws_block = atoi(e);

@@ -241,6 +241,8 @@ Solver::Solver(const KernelConfig &cfg, const pypde_b200_devfn *F, const pypde_b
   // lane holds one side's state and gradient only: 3-D Navier-Stokes at 32 x 128^2,
   // k_wavespeeds + k_faces 18.4 + 2.6 ms against 15.8 ms (profiles/r2_c5_sweep.txt), and one
   // pass over the 58 GB of traces instead of two.
+  if (const char *e = getenv("PYPDE_B200_WS_SMEM_PAD"))
+    ws_pad_ = atol(e);
   fused_faces_ = cfg_.V <= 5 && !(cfg_.secondOrder && cfg_.useB);
   if (const char *e = getenv("PYPDE_B200_FUSED_FACES"))
     fused_faces_ = *e != '0';
@@ -889,7 +891,17 @@ void Solver::step_body() {
   } else if (cfg_.useF && cfg_.flux == 0) {
     long total = ncellw_ * 2 * nd;
     void *args[] = {&traces_.p, &ws_.p, &ncellw_, &g_};
-    launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, 0, args,
+    // (experiment knob: unused dynamic shared memory caps the resident blocks per SM — the
+    //  n > 5 eigen-solves keep their matrices in local memory, and how many of them are in
+    //  flight decides whether that working set stays in L2; tools/variant_sweep.py eig)
+    const long pad = ws_pad_;
+    if (pad > 48 * 1024 && !ws_pad_set_) {
+      check(driver().FuncSetAttribute(mod_->k_wavespeeds,
+                                      CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)pad),
+            "cuFuncSetAttribute(k_wavespeeds smem pad)");
+      ws_pad_set_ = true;
+    }
+    launch(mod_->k_wavespeeds, grid_for(total, cfg_.ws_block), cfg_.ws_block, (size_t)pad, args,
            "k_wavespeeds");
   }
   if ((cfg_.useF || cfg_.useB) && !(cfg_.useF && cfg_.flux == 0 && fused_faces_)) {

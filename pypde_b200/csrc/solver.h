@@ -127,6 +127,8 @@ private:
   void launch(CUfunction f, unsigned grid, unsigned block, size_t smem, void **args,
               const char *name, unsigned grid_y = 1, unsigned grid_z = 1);
   bool profiling_ = false;
+  bool ws_pad_set_ = false;
+  long ws_pad_ = 0; // PYPDE_B200_WS_SMEM_PAD
   struct Rec {
     const char *name;
     CUevent a, b;

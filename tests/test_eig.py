@@ -59,19 +59,26 @@ def spectrum_case(n, kind, rng):
 @pytest.mark.parametrize('kind', ['real', 'euler', 'complex_dominant', 'complex_small'])
 def test_known_spectra(n, kind):
     rng = np.random.default_rng(100 * n + len(kind))
-    fast = 0
+    fast = cert = 0
     for _ in range(300):
         D, true = spectrum_case(n, kind, rng)
         A = similar(D, rng)
         r, path = rho(A)
         rq, _ = rho(A, 1)
-        fast += path
+        fast += path == 1
+        cert += path == 2
         assert abs(r - true) / true < 2e-13, (n, kind, path)
         assert abs(rq - true) / true < 2e-13
     if kind == 'euler' and 3 <= n <= 5:
         assert fast > 250          # the hyperbolic case takes the register-only path
     if n > 5:
+        # Hessenberg + certified characteristic polynomial (path 2) where the outer roots are
+        # real and simple; the QR iteration where a complex pair dominates
         assert fast == 0
+        if kind == 'real':
+            assert cert > 250
+        if kind == 'complex_dominant':
+            print(n, kind, cert)
 
 
 def euler_jacobian(q, d, nd, g=1.4):
@@ -300,18 +307,22 @@ def test_gpr_system_matrices(ndim):
         q[14:17] += 0.01 * rng.standard_normal(3)
         states.append(q)
     active = []
+    fast = 0
     for q in states:
         for d in range(ndim):
             M = _fd_system_matrix(s['F'], s['B'], q, d, ndim)
             want = np.abs(np.linalg.eigvals(M)).max()
             got, path = rho(M)
             full, _ = rho(M, qr_only=1)
-            assert path == 0
+            assert path in (0, 2)
+            fast += path == 2
             assert abs(got - want) <= 1e-12 * want, (ndim, d, got, want)
             assert abs(got - full) <= 1e-12 * want
             active.append(17 - sum(1 for i in range(17)
                                    if not np.any(np.delete(M[i], i)) or not np.any(np.delete(M[:, i], i))))
     assert max(active) < 17          # (first sweep only: the permutation step always finds some)
+    # hyperbolic: the certified characteristic-polynomial path decides nearly all of them
+    assert fast >= 0.9 * len(active)
 
 
 @pytest.mark.parametrize('n', [6, 9, 17])
@@ -342,3 +353,47 @@ def test_deflation_structures(n):
         want = np.abs(np.linalg.eigvals(A)).max()
         got, _ = rho(A)
         assert abs(got - want) <= 2e-12 * max(want, 1e-300), (n, kind, got, want)
+
+
+@pytest.mark.parametrize('n', [6, 9, 11, 17])
+def test_hess_poly_certificate_edges(n):
+    """n > 5: spectra at the edge of what the characteristic-polynomial path may certify — a
+    complex pair just inside / just outside the outer real root, a double outer root, outer
+    roots of equal modulus, large and small scales, a shifted (supersonic) spectrum.  Whatever
+    path decides, the result is LAPACK's."""
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(240):
+        kind = trial % 8
+        ev = list(rng.uniform(-0.6, 0.6, n))
+        D = np.zeros((n, n))
+        blocks = []
+        if kind in (0, 1, 2, 3):     # complex pair of modulus 1 +- delta against real roots +-1
+            delta = [1e-2, 1e-4, -1e-4, -1e-2][kind]
+            ev = [1., -1.] + ev[:n - 4]
+            th = rng.uniform(0.3, 2.8)
+            r = 1. + delta
+            blocks.append(r * np.array([[np.cos(th), np.sin(th)], [-np.sin(th), np.cos(th)]]))
+        elif kind == 4:              # double outer root
+            ev = [1., 1., -0.9] + ev[:n - 3]
+        elif kind == 5:              # +-1 exactly balanced
+            ev = [1., -1.] + ev[:n - 2]
+        elif kind == 6:              # supersonic: everything shifted far to one side
+            ev = [x + 7. for x in [1., -1.] + ev[:n - 2]]
+        else:                        # scales
+            s = 10.**rng.integers(-8, 9)
+            ev = [s * x for x in [1., -0.97] + ev[:n - 2]]
+        k = 0
+        for b in blocks:
+            D[k:k + 2, k:k + 2] = b
+            k += 2
+        for x in ev:
+            D[k, k] = x
+            k += 1
+        assert k == n
+        A = similar(D, rng)
+        want = np.abs(np.linalg.eigvals(A)).max()
+        for mode in (0, 3, 4):
+            got, path = rho(A, mode)
+            assert abs(got - want) <= 5e-12 * want, (n, kind, mode, path, got, want)
+            if kind in (0, 1, 4):
+                assert path == 0, (n, kind, mode)     # must not be certified

@@ -144,6 +144,35 @@ def test_kernel_variants_agree_bit_for_bit(name, env):
     assert np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize('name', ['gpr1d_N2_stiff', 'gpr2d_N2_stiff'])
+def test_large_system_eigen_paths(golden, name):
+    """V > 5 (GPR, V = 17): the wave speeds come from the two-pass Jacobian (active block
+    stored compact), the permutation step on bit masks and the certified characteristic
+    polynomial of the Hessenberg form.  Each step switched off in turn (PDE_EIG_TWOPASS=0: the
+    full matrix in local memory, the same bits; PDE_EIG_MASK=0: isolated eigenvalues found by
+    row / column exchanges; PDE_EIG_HESS_POLY=0: the QR iteration on every block;
+    PDE_EIG_DEFLATE=0: round 1's QR iteration on the full matrix) must give the reference's
+    result within the stated tolerance, and the default's to rounding."""
+    c = cases.solver_cases()[name]
+    want = golden['solver'][name]
+    tol = parity_tolerance(golden['solver'], name, 1e-8)
+    outs = {}
+    for defs in ('', 'PDE_EIG_TWOPASS=0', 'PDE_EIG_MASK=0', 'PDE_EIG_HESS_POLY=0',
+                 'PDE_EIG_DEFLATE=0'):
+        os.environ['PYPDE_B200_KEEP_SOLVER'] = '0'
+        if defs:
+            os.environ['PYPDE_B200_EXTRA_DEFINES'] = defs
+        try:
+            outs[defs] = run_gpu(c)[0]
+        finally:
+            del os.environ['PYPDE_B200_KEEP_SOLVER']
+            os.environ.pop('PYPDE_B200_EXTRA_DEFINES', None)
+        assert rel_linf(outs[defs][0], want) < tol, defs
+    assert np.array_equal(outs[''], outs['PDE_EIG_TWOPASS=0'])
+    for defs in outs:
+        assert rel_linf(outs[defs][0], outs[''][0]) < 1e-9, defs
+
+
 def test_weno_solver_on_a_cuda_tensor():
     """weno_solver(torch CUDA tensor) -> CUDA tensor, bit-identical to the host-buffer call."""
     import torch

@@ -31,6 +31,8 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
         'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed',
         'smsp__cycles_elapsed.max', 'lts__t_bytes.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum',
         'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
         'smsp__thread_inst_executed_per_inst_executed.ratio']
 stalls = [h for h in hdr if h.startswith('smsp__pcsamp_warps_issue_stalled')

@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4', 'eig2': 'c4'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512, 'eig2': 512}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -29,19 +29,33 @@ cells = int(np.prod(Q0.shape[:-1]))
 
 SETS = {}
 SETS['eig'] = [
+    ('two-pass Jacobian, active block stored compact (default)', {}),
+    ('one pass: full matrix in local memory, then gathered', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_TWOPASS=0'}),
+    ('  permutation step by exchanges in memory instead of bit masks', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_MASK=0'}),
+    ('  QR iteration instead of the certified characteristic polynomial', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_HESS_POLY=0'}),
     ('round 1: QR iteration on the full matrix', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_DEFLATE=0'}),
-    ('isolated eigenvalues first, QR on the active block', {}),
-    ('  + ws_block 128 x 4', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
-    ('  + ws_block 256 x 2', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+    ('default, k_wavespeeds 128 x 4 blocks per SM', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
+    ('default, 128 x 3 blocks per SM (smem pad)', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4', 'PYPDE_B200_WS_SMEM_PAD': '73000'}),
+    ('default, 128 x 2 blocks per SM (smem pad)', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4', 'PYPDE_B200_WS_SMEM_PAD': '110000'}),
+    ('default, 128 x 1 block per SM (smem pad)', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '4', 'PYPDE_B200_WS_SMEM_PAD': '200000'}),
+    ('default, 256 x 1 block per SM (smem pad)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '2', 'PYPDE_B200_WS_SMEM_PAD': '120000'}),
 ]
-SETS['occ'] = [   # occupancy against registers for the QR-bound kernels
+SETS['eig2'] = [   # details of the n > 5 path
     ('default', {}),
-    ('k_wavespeeds 256 x 3 (85 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '3'}),
-    ('k_wavespeeds 256 x 4 (64 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
-    ('k_wavespeeds 128 x 6 (85 registers)', {'PYPDE_B200_WS_BLOCK': '128', 'PYPDE_B200_WS_MINBLOCKS': '6'}),
-    ('k_faces 4 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=4'}),
-    ('k_faces 5 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=5'}),
-    ('k_faces 6 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=6'}),
+    ('pass 1 of the Jacobian as a loop (one inlined flux instead of V)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_PASS1_ROLLED=1'}),
+    ('active block with row pitch m instead of V', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_PITCH_FULL=0'}),
+    ('Hessenberg reduction with zero-factor skips', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_HESS_SKIP=1'}),
+    ('at most 3 balancing sweeps instead of 6', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_BAL_SWEEPS=3'}),
+    ('at most 1 balancing sweep', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_BAL_SWEEPS=1'}),
+]
+SETS['occ'] = [   # occupancy against registers for the n > 5 wave-speed kernel (latency-bound per thread)
+    ('default: k_wavespeeds 512 x 1 (128 registers)', {}),
+    ('640 x 1 (96 registers)', {'PYPDE_B200_WS_BLOCK': '640', 'PYPDE_B200_WS_MINBLOCKS': '1'}),
+    ('768 x 1 (80 registers)', {'PYPDE_B200_WS_BLOCK': '768', 'PYPDE_B200_WS_MINBLOCKS': '1'}),
+    ('256 x 3 (85 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '3'}),
+    ('1024 x 1 (64 registers)', {'PYPDE_B200_WS_BLOCK': '1024', 'PYPDE_B200_WS_MINBLOCKS': '1'}),
+    ('512 x 2 (64 registers)', {'PYPDE_B200_WS_BLOCK': '512', 'PYPDE_B200_WS_MINBLOCKS': '2'}),
+    ('256 x 4 (64 registers)', {'PYPDE_B200_WS_BLOCK': '256', 'PYPDE_B200_WS_MINBLOCKS': '4'}),
 ]
 SETS['gprstiff'] = [
     ('default (254 registers, 2 blocks of 4 warps per SM)', {}),

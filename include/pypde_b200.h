@@ -108,6 +108,11 @@ int pypde_b200_host_spectral_radius_pair(const double *A0, const double *A1, int
 /* Same, for the Osher/Roe dissipation y = |A| x = Re(R |Lambda| R^-1 x). */
 int pypde_b200_host_abs_matrix_apply(const double *A, int n, const double *x, double *y);
 
+/* Same, the projector form for n = 3..5 the face kernels try first (two simple outer real
+ * eigenvalues + one tight cluster, the spectrum of an Euler-type system): 0 = certified and
+ * y written, 2 = not certified (the kernel then takes the general routine above). */
+int pypde_b200_host_abs_matrix_apply_poly(const double *A, int n, const double *x, double *y);
+
 /* Stand-alone reconstruction with input and output resident in HBM (the device-pointer
  * form of weno_solver, reference api.cpp:32-48): u_dev holds prod(nX) V doubles, ret_dev
  * prod(nX_d - 2(N-1)) N^ndim V doubles; enqueued on `stream` (a CUstream / cudaStream_t,

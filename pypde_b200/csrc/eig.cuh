@@ -1608,6 +1608,156 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
 }
 
 // ---------------------------------------------------------------------------
+// D2 fast path (3 <= n <= 5): y = |A| x without an eigen-decomposition, for the spectrum of
+// an Euler-type system — two simple outer real eigenvalues lam_m < lam_p and everything else
+// in one tight cluster around a real centre a (the n - 2 copies of the convective speed, split
+// at the 1e-8 level by the finite-difference Jacobian).  With the spectral projectors
+//   P_i = adj(lam_i I - A) / p'(lam_i)            (simple eigenvalue lam_i)
+// and the cluster component w = x - P_m x - P_p x,
+//   |A| x = |lam_m| P_m x + |lam_p| P_p x + |a| w.
+// adj(y I - B) x = sum_k y^k v_k with v_(n-1) = x, v_(k-1) = B v_k + c_k x (the
+// Faddeev-LeVerrier recurrence applied to a vector: n - 1 matrix-vector products, B = A - mu I
+// and c the characteristic polynomial poly_setup gives), so the whole product is ~10 n^2
+// multiply-adds in registers where the real-Schur route (elmhes / hqr2 / back-substitution / QR
+// solve, in local memory) takes thousands.  It is also the more accurate of the two on exactly
+// this spectrum: a triple eigenvalue leaves hqr2's back-substituted vectors numerically dependent
+// (sqrt(eps)-level errors, tests/test_eig.py), whereas the cluster never needs its own vectors.
+// Certificates — any failure returns false and the caller takes the general routine:
+//   * both outer roots found by the monotone iteration, distinct, well conditioned
+//     (kappa eps <~ 1e-13);
+//   * the remaining n - 2 roots within 1e-4 of the scale around their mean (Fujiwara's bound on
+//     the remainder polynomial shifted to its mean), and that cluster separated from both
+//     outer roots by more than 1e-3 of the scale;
+//   * A acts on w as a I to 1e-6 of the scale: ||A w - a w|| <= 1e-6 scale ||x|| (a direct
+//     measurement; the bound from the coefficients cannot resolve a cluster below eps^(1/3)).
+// What remains is the spread of the cluster itself: the result differs from R |Lambda| R^-1 x
+// by at most that spread times ||w|| — for a finite-difference Jacobian its own rounding noise.
+// ---------------------------------------------------------------------------
+#ifndef PDE_ABS_POLY
+#define PDE_ABS_POLY 1
+#endif
+template <int n> EIG_FN bool abs_matrix_apply_poly(const double *A, const double *x, double *y) {
+  double mu, c[n];
+  poly_setup<n>(A, mu, c);
+  if (!(c[n - 2] < 0.))
+    return false;
+  const double x0 = sqrt(-2. * c[n - 2] * ((n - 1.) / n)) * (1. + 1e-3);
+  double cn[n];
+#pragma unroll
+  for (int k = 0; k < n; k++)
+    cn[k] = ((n - k) & 1) ? -c[k] : c[k];
+  double yp, ym;
+  if (!PolyRoots<n>::iterate(c, x0, false, yp))
+    return false;
+  if (!PolyRoots<n>::iterate(cn, x0, false, ym))
+    return false;
+  ym = -ym;
+  const double ayp = fabs(yp), aym = fabs(ym);
+  const double sc = fabs(mu) + (ayp > aym ? ayp : aym);
+  if (!(sc > 0.) || !(sc <= 1e150))
+    return false;
+  // p' at both roots and their conditioning
+  double dpp = 0., dpm = 0.;
+  {
+    double pp = 1., pm = 1., abp = 1., abm = 1.;
+#pragma unroll
+    for (int k = n - 1; k >= 0; k--) {
+      dpp = fma(dpp, yp, pp);
+      pp = fma(pp, yp, c[k]);
+      abp = fma(abp, ayp, fabs(c[k]));
+      dpm = fma(dpm, ym, pm);
+      pm = fma(pm, ym, c[k]);
+      abm = fma(abm, aym, fabs(c[k]));
+    }
+    if (!(abp <= 400. * ayp * fabs(dpp)) || !(abm <= 400. * aym * fabs(dpm)))
+      return false;
+  }
+  // the remainder p / ((y - yp)(y - ym)): centre and radius of its roots
+  double ay = 0., r = 0.;
+  {
+    double b[n], e[n];
+    double carry = 1.;
+#pragma unroll
+    for (int k = n - 1; k >= 1; k--) {
+      carry = fma(carry, yp, c[k]);
+      b[k - 1] = carry;
+    }
+    carry = 1.;
+#pragma unroll
+    for (int k = n - 2; k >= 1; k--) {
+      carry = fma(carry, ym, b[k]);
+      e[k - 1] = carry;
+    }
+    if (n == 3) {
+      ay = -e[0];
+    } else if (n == 4) { // y^2 + e1 y + e0
+      ay = -0.5 * e[1];
+      r = sqrt(fabs(fma(-0.25 * e[1], e[1], e[0])));
+    } else { // y^3 + e2 y^2 + e1 y + e0 about its mean: z^3 + t1 z + t0
+      ay = -e[2] * (1. / 3.);
+      const double t1 = fma(-e[2] * (1. / 3.), e[2], e[1]);
+      const double t0 = fma(fma(fma(1., ay, e[2]), ay, e[1]), ay, e[0]);
+      r = 2. * fmax(sqrt(fabs(t1)), cbrt(0.5 * fabs(t0)));
+    }
+  }
+  if (!(r <= 1e-4 * sc) || !(yp - ay > 1e-3 * sc + r) || !(ay - ym > 1e-3 * sc + r))
+    return false;
+  // v_k = M_k x and adj(y I - B) x at both roots (Horner over k, leading term v_(n-1) = x)
+  double v[n], gp[n], gm[n], xmax = 0.;
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    v[i] = x[i];
+    gp[i] = x[i];
+    gm[i] = x[i];
+    xmax = fmax(xmax, fabs(x[i]));
+  }
+#pragma unroll
+  for (int k = n - 1; k >= 1; k--) {
+    double t[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      double acc = fma(-mu, v[i], c[k] * x[i]);
+#pragma unroll
+      for (int j = 0; j < n; j++)
+        acc = fma(A[i * n + j], v[j], acc);
+      t[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      v[i] = t[i];
+      gp[i] = fma(gp[i], yp, t[i]);
+      gm[i] = fma(gm[i], ym, t[i]);
+    }
+  }
+  const double rp = 1. / dpp, rm = 1. / dpm;
+  const double a = mu + ay, lp = fabs(mu + yp), lm = fabs(mu + ym);
+  double w[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    gp[i] *= rp;
+    gm[i] *= rm;
+    w[i] = (x[i] - gp[i]) - gm[i];
+  }
+  // A w - a w: how far A is from a I on the cluster component
+  double dev = 0.;
+#pragma unroll
+  for (int i = 0; i < n; i++) {
+    double acc = -a * w[i];
+#pragma unroll
+    for (int j = 0; j < n; j++)
+      acc = fma(A[i * n + j], w[j], acc);
+    dev = fmax(dev, fabs(acc));
+  }
+  if (!(dev <= 1e-6 * sc * xmax))
+    return false;
+  const double aa = fabs(a);
+#pragma unroll
+  for (int i = 0; i < n; i++)
+    y[i] = fma(lp, gp[i], fma(lm, gm[i], aa * w[i]));
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // D2: y = |A| x for a general real n x n matrix, |A| = R |Lambda| R^-1 — the
 // dissipation matrix of the Osher and Roe fluxes (reference fluxes.cpp:36-41,
 // 64-69: Eigen EigenSolver + complex column-pivoted QR solve, real part taken).
@@ -2065,6 +2215,18 @@ template <int n> EIG_FN_NOINLINE bool abs_matrix_apply(double *a, const double *
   return true;
 #undef A_
 #undef Z_
+}
+
+// The dissipation product as the face kernels call it: the projector form where it certifies,
+// the real-Schur route otherwise.  a is destroyed.
+template <int n> EIG_FN bool abs_matrix_apply_any(double *a, const double *x, double *y) {
+#if PDE_ABS_POLY
+  if (n >= 3 && n <= 5) {
+    if (abs_matrix_apply_poly<(n >= 3 && n <= 5) ? n : 3>(a, x, y))
+      return true;
+  }
+#endif
+  return abs_matrix_apply<n>(a, x, y);
 }
 
 #endif // PYPDE_B200_EIG_CUH

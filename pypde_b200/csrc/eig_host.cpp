@@ -63,6 +63,27 @@ extern "C" int pypde_b200_host_abs_matrix_apply(const double *A, int n, const do
   return ok ? 0 : 2;
 }
 
+// The projector form of |A| x for n = 3..5 (abs_matrix_apply_poly): 0 certified (y written),
+// 2 not certified (the device then takes abs_matrix_apply).
+extern "C" int pypde_b200_host_abs_matrix_apply_poly(const double *A, int n, const double *x,
+                                                     double *y) {
+  if (n < 3 || n > 5 || !A || !x || !y)
+    return 1;
+  bool ok = false;
+  switch (n) {
+  case 3:
+    ok = abs_matrix_apply_poly<3>(A, x, y);
+    break;
+  case 4:
+    ok = abs_matrix_apply_poly<4>(A, x, y);
+    break;
+  case 5:
+    ok = abs_matrix_apply_poly<5>(A, x, y);
+    break;
+  }
+  return ok ? 0 : 2;
+}
+
 // Two matrices through the two-sided polynomial path (what k_faces_fused runs per face
 // point); ok[s] = 0 where that path defers to the QR iteration (rho[s] then comes from it).
 extern "C" int pypde_b200_host_spectral_radius_pair(const double *A0, const double *A1, int n,

@@ -397,3 +397,84 @@ def test_hess_poly_certificate_edges(n):
             assert abs(got - want) <= 5e-12 * want, (n, kind, mode, path, got, want)
             if kind in (0, 1, 4):
                 assert path == 0, (n, kind, mode)     # must not be certified
+
+
+def abs_apply_poly(A, x):
+    lib = get_cdll()
+    A = np.ascontiguousarray(A, dtype=float)
+    x = np.ascontiguousarray(x, dtype=float)
+    y = np.zeros_like(x)
+    rc = lib.pypde_b200_host_abs_matrix_apply_poly(A.ctypes.data_as(P), A.shape[0],
+                                                   x.ctypes.data_as(P), y.ctypes.data_as(P))
+    return y, rc
+
+
+@pytest.mark.parametrize('n', [3, 4, 5])
+@pytest.mark.parametrize('kind', ['real', 'euler', 'complex_dominant', 'complex_small', 'random'])
+def test_abs_matrix_apply_projector_form(n, kind):
+    """|A| x from the spectral projectors of the two outer eigenvalues + the cluster centre
+    (abs_matrix_apply_poly): whenever it certifies, the result is T |D| T^-1 x; on the Euler
+    spectrum (v-c, v x (n-2), v+c) it certifies as a rule and — unlike the real-Schur route,
+    whose vectors degenerate on the multiple eigenvalue — to rounding."""
+    rng = np.random.default_rng(31 * n + len(kind))
+    certified = 0
+    for _ in range(300):
+        x = rng.standard_normal(n)
+        if kind == 'random':
+            A = rng.standard_normal((n, n))
+            true = abs_apply_numpy(A, x)
+        else:
+            D, _ = spectrum_case(n, kind, rng)
+            Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+            T = Q @ np.diag(10**rng.uniform(-0.5, 0.5, n))
+            Ti = np.linalg.inv(T)
+            A = T @ D @ Ti
+            if kind.startswith('complex'):
+                m = np.hypot(D[0, 0], D[0, 1])
+                absD = np.diag(np.concatenate([[m, m], np.abs(np.diag(D)[2:])]))
+            else:
+                absD = np.diag(np.abs(np.diag(D)))
+            true = T @ absD @ (Ti @ x)
+        y, rc = abs_apply_poly(A, x)
+        assert rc in (0, 2)
+        if rc == 0:
+            certified += 1
+            scale = np.abs(np.linalg.eigvals(A)).max() * np.abs(x).max()
+            assert np.abs(y - true).max() <= 2e-12 * scale, (n, kind)
+    if kind == 'euler':
+        assert certified >= 290
+    if kind in ('real', 'random') and n == 5:
+        assert certified <= 5            # three distinct inner eigenvalues are no cluster
+
+
+@pytest.mark.parametrize('nd', [1, 2, 3])
+def test_abs_matrix_apply_projector_form_on_euler_jacobians(nd):
+    """Finite-difference Euler Jacobians (the cluster split at the 1e-8 level, gas at rest
+    included): the projector form certifies and agrees with LAPACK's R |Lambda| R^-1 x to
+    the spread of the cluster (LAPACK's own result moves by as much when the noise changes)."""
+    rng = np.random.default_rng(5 + nd)
+    n = nd + 2
+    worst = 0.
+    total = certified = 0
+    for trial in range(200):
+        rho_, p = rng.uniform(0.2, 3.), rng.uniform(0.2, 3.)
+        v = rng.standard_normal(nd) * rng.choice([0., 0.3, 1.])
+        q = np.concatenate([[rho_, p / 0.4 + 0.5 * rho_ * v @ v], rho_ * v])
+        for d in range(nd):
+            A, _ = euler_jacobian(q, d, nd)
+            # forward-difference noise of the size the device sees
+            A = A * (1. + 1e-8 * rng.standard_normal(A.shape))
+            x = rng.standard_normal(n)
+            y, rc = abs_apply_poly(A, x)
+            c = np.sqrt(1.4 * p / rho_)
+            if abs(abs(v[d]) - c) < 2e-3 * (abs(v[d]) + c):
+                continue                  # sonic point: the cluster touches an outer root
+            total += 1
+            if rc:
+                continue                  # (high Mach number: the noise spreads the cluster)
+            certified += 1
+            true = abs_apply_numpy(A, x)
+            scale = (abs(v[d]) + c) * np.abs(x).max()
+            worst = max(worst, np.abs(y - true).max() / scale)
+    assert certified >= 0.97 * total
+    assert worst < 1e-6          # the spread of the noisy cluster times the vectors' condition

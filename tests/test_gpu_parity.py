@@ -173,6 +173,33 @@ def test_large_system_eigen_paths(golden, name):
         assert rel_linf(outs[defs][0], outs[''][0]) < 1e-9, defs
 
 
+@pytest.mark.parametrize('name', ['euler1d_smooth_N3_osher', 'euler2d_smooth_N2_roe',
+                                  'sod_short_N2_osher', 'ns1d_smooth_N2_osher',
+                                  'reactive2d_disc_N3_stiff_osher'])
+def test_dissipation_matrix_paths(golden, name):
+    """Roe / Osher: |A| (qL - qR) from the spectral projectors of the two outer eigenvalues
+    and the cluster centre (abs_matrix_apply_poly, the default for V = 3..5) and from the
+    real-Schur route on every matrix (PDE_ABS_POLY=0) — both within the stated tolerance of
+    the reference, and of each other to the spread of the finite-difference cluster."""
+    c = cases.solver_cases()[name]
+    want = golden['solver'][name]
+    tol = parity_tolerance(golden['solver'], name, 1e-8 if c.get('stiff') else 1e-10)
+    outs = {}
+    for defs in ('', 'PDE_ABS_POLY=0'):
+        os.environ['PYPDE_B200_KEEP_SOLVER'] = '0'
+        if defs:
+            os.environ['PYPDE_B200_EXTRA_DEFINES'] = defs
+        try:
+            outs[defs] = run_gpu(c)[0]
+        finally:
+            del os.environ['PYPDE_B200_KEEP_SOLVER']
+            os.environ.pop('PYPDE_B200_EXTRA_DEFINES', None)
+        err = rel_linf(outs[defs][0], want)
+        print('%s [%s]: GPU vs reference %.2e (tolerance %.2e)' % (name, defs or 'default', err, tol))
+        assert err < tol, defs
+    assert rel_linf(outs[''][0], outs['PDE_ABS_POLY=0'][0]) < 1e-8
+
+
 def test_weno_solver_on_a_cuda_tensor():
     """weno_solver(torch CUDA tensor) -> CUDA tensor, bit-identical to the host-buffer call."""
     import torch

@@ -12,6 +12,8 @@ for d in PDE_EIG_TWOPASS=0 PDE_EIG_MASK=0 PDE_EIG_HESS_POLY=0 PDE_EIG_DEFLATE=0;
   PYPDE_B200_EXTRA_DEFINES=$d python -m pytest tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider \
     -k "test_solver_golden and gpr" > /dev/null 2>&1
 done
+PYPDE_B200_EXTRA_DEFINES=PDE_ABS_POLY=0 python -m pytest tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider \
+  -k "test_solver_golden and (osher or roe)" > /dev/null 2>&1
 for c in c1 c2 c3 c4 c5; do python tools/prof_config.py $c 1 16 > /dev/null 2>&1; done
 for s in "$@"; do python tools/variant_sweep.py $s x 16 1 2>&1 | grep -c failed; done
 ls $PYPDE_B200_CACHE | wc -l

@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4', 'eig2': 'c4'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512, 'eig2': 512}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4', 'eig2': 'c4', 'osher': 'c3'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512, 'eig2': 512, 'osher': 512}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -47,6 +47,12 @@ SETS['eig2'] = [   # details of the n > 5 path
     ('Hessenberg reduction with zero-factor skips', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_HESS_SKIP=1'}),
     ('at most 3 balancing sweeps instead of 6', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_BAL_SWEEPS=3'}),
     ('at most 1 balancing sweep', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_EIG_BAL_SWEEPS=1'}),
+]
+SETS['osher'] = [   # Osher / Roe dissipation |A| x for V = 3..5
+    ('projector form where it certifies (default)', {}),
+    ('real-Schur route on every matrix (elmhes / hqr2 / QR solve)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_ABS_POLY=0'}),
+    ('default, k_faces 4 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=4'}),
+    ('default, k_faces 2 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=2'}),
 ]
 SETS['occ'] = [   # occupancy against registers for the n > 5 wave-speed kernel (latency-bound per thread)
     ('default: k_wavespeeds 512 x 1 (128 registers)', {}),

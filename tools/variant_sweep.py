@@ -18,8 +18,8 @@ from pypde_b200.handle import Solver  # noqa: E402
 from pypde_b200.systems import cuda_sources  # noqa: E402
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'stiff'
-name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4', 'eig2': 'c4', 'osher': 'c3'}[which]
-size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512, 'eig2': 512, 'osher': 512}[which]
+name = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != 'x' else {'stiff': 'c3', 'eig': 'c4', 'faces': 'c2', 'weno3d': 'c5', 'c5': 'c5', 'occ': 'c4', 'gprstiff': 'c4', 'eig2': 'c4', 'osher': 'c3', 'stiff2': 'c3'}[which]
+size = int(sys.argv[3]) if len(sys.argv) > 3 else {'stiff': 512, 'eig': 256, 'faces': 2048, 'weno3d': 128, 'c5': 128, 'occ': 256, 'gprstiff': 512, 'eig2': 512, 'osher': 512, 'stiff2': 512}[which]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = bench.CONFIGS[name]
 os.environ['PYPDE_B200_QUIET'] = '1'
@@ -53,6 +53,10 @@ SETS['osher'] = [   # Osher / Roe dissipation |A| x for V = 3..5
     ('real-Schur route on every matrix (elmhes / hqr2 / QR solve)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_ABS_POLY=0'}),
     ('default, k_faces 4 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=4'}),
     ('default, k_faces 2 blocks per SM', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_FACES_MINBLOCKS=2'}),
+]
+SETS['stiff2'] = [   # the Gram-Schmidt loop of k_dg_stiff
+    ('next basis vector prefetched during the reduction (default)', {}),
+    ('no prefetch', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_PREFETCH=0'}),
 ]
 SETS['occ'] = [   # occupancy against registers for the n > 5 wave-speed kernel (latency-bound per thread)
     ('default: k_wavespeeds 512 x 1 (128 registers)', {}),

@@ -59,7 +59,8 @@ SETS['stiff2'] = [   # the Gram-Schmidt loop of k_dg_stiff
     ('no prefetch', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_PREFETCH=0'}),
     ('quotients instead of reciprocal multiplies in the Krylov loop', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_RECIP=0'}),
     ('the direction z re-read from the basis instead of kept in registers', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_ZREG=0'}),
-    ('all three off (the kernel of session S)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_ZREG=0;PDE_STIFF_RECIP=0;PDE_STIFF_PREFETCH=0'}),
+    ('DMUL + DADD pairs instead of fused multiply-adds in the Krylov linear algebra', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_FMA=0'}),
+    ('all four off (the kernel of session S)', {'PYPDE_B200_EXTRA_DEFINES': 'PDE_STIFF_ZREG=0;PDE_STIFF_RECIP=0;PDE_STIFF_PREFETCH=0;PDE_STIFF_FMA=0'}),
 ]
 SETS['occ'] = [   # occupancy against registers for the n > 5 wave-speed kernel (latency-bound per thread)
     ('default: k_wavespeeds 512 x 1 (128 registers)', {}),

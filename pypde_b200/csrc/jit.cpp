@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <dlfcn.h>
+#include <limits.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -91,14 +92,21 @@ std::string shipped_cache_dir() {
   Dl_info info;
   if (!dladdr((void *)&shipped_cache_dir, &info) || !info.dli_fname)
     return std::string();
-  std::string d(info.dli_fname);
+  // (the library's real location: a symlink to it elsewhere — the reference package's
+  //  pypde/build/libpypde.so of INTEGRATION.md 1 — still finds the cubins shipped with it)
+  char real[PATH_MAX];
+  std::string d(realpath(info.dli_fname, real) ? real : info.dli_fname);
   const size_t slash = d.rfind('/');
   if (slash == std::string::npos)
     return std::string();
   d = d.substr(0, slash) + "/cubin_cache";
   struct stat st;
-  if (lstat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() ||
-      (st.st_mode & 022) != 0)
+  const int rc = lstat(d.c_str(), &st);
+  if (getenv("PYPDE_B200_CACHE_DEBUG"))
+    fprintf(stderr, "pypde_b200: library '%s', shipped cache '%s': lstat %d, mode %o, uid %d (caller %d)\n",
+            info.dli_fname, d.c_str(), rc, rc == 0 ? (unsigned)st.st_mode : 0u,
+            rc == 0 ? (int)st.st_uid : -1, (int)getuid());
+  if (rc != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() || (st.st_mode & 022) != 0)
     return std::string();
   return d;
 }
@@ -441,6 +449,9 @@ std::vector<char> build_cubin(const KernelConfig &cfg, const pypde_b200_devfn *F
   }
   if (!getenv("PYPDE_B200_NO_DISK_CACHE")) {
     const std::string shipped = shipped_cache_dir();
+    if (getenv("PYPDE_B200_CACHE_DEBUG"))
+      fprintf(stderr, "pypde_b200: cubin %s: not in '%s'; shipped cache '%s'\n", key.c_str(),
+              dir.c_str(), shipped.c_str());
     if (!shipped.empty() && read_file(shipped + "/" + key + ".cubin", cubin)) {
       std::lock_guard<std::mutex> lk(g_cache_mutex);
       g_cache[key] = cubin;

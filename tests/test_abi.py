@@ -196,3 +196,37 @@ print(len(os.listdir(os.environ['PYPDE_B200_CACHE_REAL'])))
     os.symlink(private, link)
     assert run(link, private, 0o700) == 0               # a symlink: refused
     assert run(private, private, 0o700) == 1            # a private directory: used
+
+
+def test_shipped_cubins_are_found_through_a_symlink_to_the_library(tmp_path):
+    """INTEGRATION.md 1 places libpypde.so into the reference package as a symlink
+    (pypde/build/libpypde.so).  Loaded through it — and by soname every later load in that
+    process resolves to the same object — the library must still look for the cubins shipped
+    next to its REAL location (<dir of the real file>/cubin_cache), not next to the link."""
+    import sys
+    from pypde_b200.utils import lib_path
+    real_dir = os.path.join(os.path.dirname(os.path.realpath(lib_path())), 'cubin_cache')
+    if not os.path.isdir(real_dir):
+        pytest.skip('no shipped cubin cache (filled by __graft_entry__.build())')
+    os.chmod(real_dir, 0o700)
+    (tmp_path / 'pypde' / 'build').mkdir(parents=True)
+    link = tmp_path / 'pypde' / 'build' / 'libpypde.so'
+    os.symlink(lib_path(), link)
+    script = '''
+import ctypes, os, sys
+ctypes.CDLL(%r)
+from pypde_b200.systems import cuda_sources
+from pypde_b200.utils import get_cdll, last_error
+F, B, S, V = cuda_sources('burgers', 1)
+n = ctypes.c_size_t()
+rc = get_cdll().pypde_b200_compile(F.pointer, None, None, 1, 2, V, 0, 0, 0, ctypes.byref(n), None,
+                                   ctypes.c_size_t(0))
+assert rc == 0, last_error()
+''' % str(link)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    empty = tmp_path / 'user_cache'
+    empty.mkdir(mode=0o700)
+    env = dict(os.environ, PYPDE_B200_CACHE=str(empty), PYPDE_B200_CACHE_DEBUG='1', PYTHONPATH=root)
+    out = subprocess.run([sys.executable, '-c', script], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "shipped cache '%s'" % real_dir in out.stderr, out.stderr

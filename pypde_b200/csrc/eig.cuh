@@ -1628,10 +1628,13 @@ EIG_FN double spectral_radius(double *a, int *path = nullptr, EigGuess *guess = 
 //   * the remaining n - 2 roots within 1e-4 of the scale around their mean (Fujiwara's bound on
 //     the remainder polynomial shifted to its mean), and that cluster separated from both
 //     outer roots by more than 1e-3 of the scale;
-//   * A acts on w as a I to 1e-6 of the scale: ||A w - a w|| <= 1e-6 scale ||x|| (a direct
-//     measurement; the bound from the coefficients cannot resolve a cluster below eps^(1/3)).
-// What remains is the spread of the cluster itself: the result differs from R |Lambda| R^-1 x
-// by at most that spread times ||w|| — for a finite-difference Jacobian its own rounding noise.
+//   * the cluster term: with the cluster clear of zero (|a| > twice that bound) all its
+//     eigenvalues share the sign of a and |A| w = sign(a) A w exactly — no approximation, any
+//     spread; around zero (gas at rest: a ~ 1e-9) it is |a| w, accepted only if A acts on w as
+//     a I to 2e-7 of the scale, ||A w - a w|| <= 2e-7 scale ||x|| (a direct measurement; the
+//     bound from the coefficients cannot resolve a cluster below eps^(1/3)).  The result then
+//     differs from R |Lambda| R^-1 x by at most that spread times ||w|| — for a
+//     finite-difference Jacobian its own rounding noise, on a term that is itself that small.
 // ---------------------------------------------------------------------------
 #ifndef PDE_ABS_POLY
 #define PDE_ABS_POLY 1
@@ -1739,21 +1742,31 @@ template <int n> EIG_FN bool abs_matrix_apply_poly(const double *A, const double
     w[i] = (x[i] - gp[i]) - gm[i];
   }
   // A w - a w: how far A is from a I on the cluster component
-  double dev = 0.;
+  double dev = 0., wmax = 0., dv[n];
 #pragma unroll
   for (int i = 0; i < n; i++) {
     double acc = -a * w[i];
 #pragma unroll
     for (int j = 0; j < n; j++)
       acc = fma(A[i * n + j], w[j], acc);
+    dv[i] = acc;
     dev = fmax(dev, fabs(acc));
+    wmax = fmax(wmax, fabs(w[i]));
   }
-  if (!(dev <= 1e-6 * sc * xmax))
-    return false;
   const double aa = fabs(a);
+  // The cluster lies within r of a (a rigorous bound).  Clear of zero (|a| > 2 r), all its
+  // eigenvalues have the sign of a and |A| w = sign(a) A w EXACTLY, whatever its spread
+  // (a complex pair inside it: to second order in its imaginary part).  Around zero the
+  // term is |a| w up to the spread itself, which must then be at rounding-noise level.
+  const bool one_signed = aa > 2. * r && aa * wmax >= 8. * dev;
+  if (!one_signed && !(dev <= 2e-7 * sc * xmax))
+    return false;
+  const double sg = a < 0. ? -1. : 1.;
 #pragma unroll
-  for (int i = 0; i < n; i++)
-    y[i] = fma(lp, gp[i], fma(lm, gm[i], aa * w[i]));
+  for (int i = 0; i < n; i++) {
+    const double yc = one_signed ? sg * fma(a, w[i], dv[i]) : aa * w[i];
+    y[i] = fma(lp, gp[i], fma(lm, gm[i], yc));
+  }
   return true;
 }
 

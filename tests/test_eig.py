@@ -478,3 +478,32 @@ def test_abs_matrix_apply_projector_form_on_euler_jacobians(nd):
             worst = max(worst, np.abs(y - true).max() / scale)
     assert certified >= 0.97 * total
     assert worst < 1e-6          # the spread of the noisy cluster times the vectors' condition
+
+
+@pytest.mark.parametrize('n', [4, 5])
+def test_projector_form_cluster_term(n):
+    """The inner eigenvalues as a cluster of any spread up to 1e-4: clear of zero the cluster
+    term is sign(a) A w — exact; straddling zero (gas at rest) it is |a| w and the result may
+    differ from R |Lambda| R^-1 x by the spread, which the guard keeps below 2e-7 of the scale."""
+    rng = np.random.default_rng(900 + n)
+    for trial in range(600):
+        spread = 10.**rng.integers(-12, -3)
+        moving = trial % 2 == 0
+        v = (rng.uniform(0.05, 1.5) * rng.choice([-1., 1.])) if moving else 0.
+        c = abs(rng.standard_normal()) + 0.2
+        ev = np.concatenate([[v - c], v + spread * rng.standard_normal(n - 2), [v + c]])
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        T = Q @ np.diag(10**rng.uniform(-0.5, 0.5, n))
+        Ti = np.linalg.inv(T)
+        A = T @ np.diag(ev) @ Ti
+        x = rng.standard_normal(n)
+        y, rc = abs_apply_poly(A, x)
+        true = T @ np.diag(np.abs(ev)) @ (Ti @ x)
+        err = np.abs(y - true).max() / ((abs(v) + c) * np.abs(x).max())
+        if moving:
+            # (a spread of 1e-4 of the scale is where the cluster definition ends)
+            assert rc == 0 or spread > 1e-5 or abs(abs(v) - c) < 3e-3 * (abs(v) + c), (trial, v, c, spread)
+            if rc == 0:
+                assert err < 1e-13, (trial, spread, err)
+        elif rc == 0:
+            assert err < max(4e-7, 10 * spread), (trial, spread, err)
